@@ -1,0 +1,167 @@
+/* speigen_b200 — C ABI of the B200-native spEigen() hot path.
+ *
+ * The reference package (dppalomar/sparseEigen) is pure R with no native interface (NAMESPACE:3-4 has
+ * no useDynLib, there is no src/).  The only interface that exists is the R closure
+ *     spEigen(X, q = 1, rho = 0.5, data = FALSE, d = NA, V = NA, thres = 1e-9)      R/spEigen.R:46
+ * returning list(vectors, standard_vectors, values)                                  R/spEigen.R:162
+ * so these entry points are what a `.Call` glue for that closure binds (INTEGRATION.md shows the glue).
+ * Plain C types only; matrices are column-major exactly as R stores them; complex numbers are
+ * interleaved {re, im} doubles (Rcomplex == double[2]).  The library never keeps caller pointers after
+ * a call returns and never frees caller memory.  Errors are returned as codes, never thrown/longjmp'd.
+ */
+#ifndef SPEIGEN_B200_H
+#define SPEIGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPEIGEN_ABI_VERSION 1
+
+/* ---- status codes: 1..7 mirror the reference's stop() conditions ------------------------------ */
+#define SPEIGEN_OK 0
+#define SPEIGEN_ERR_UNIVARIATE 1      /* "Data is univariate!"                         R/spEigen.R:52 */
+#define SPEIGEN_ERR_NA 2              /* "This function cannot handle NAs."            R/spEigen.R:53 */
+#define SPEIGEN_ERR_Q 3               /* "q should be a positive integer."             R/spEigen.R:54 */
+#define SPEIGEN_ERR_RHO 4             /* "rho should be positive."                     R/spEigen.R:55 */
+#define SPEIGEN_ERR_RANK 5            /* "q should not be larger than rank(X)."        R/spEigen.R:69,79 */
+#define SPEIGEN_ERR_NOT_SYMMETRIC 6   /* "The covariance matrix is not symmetric."     R/spEigen.R:75 */
+#define SPEIGEN_ERR_NOT_PD 7          /* "The covariance matrix is not PD."            R/spEigen.R:77 */
+#define SPEIGEN_ERR_CUDA 20
+#define SPEIGEN_ERR_NCCL 21
+#define SPEIGEN_ERR_NO_DEVICE 22      /* no CUDA device: there is NO CPU fallback */
+#define SPEIGEN_ERR_ARG 23
+#define SPEIGEN_ERR_NOMEM 24
+#define SPEIGEN_ERR_UNSUPPORTED 25
+
+/* ---- configuration: the constants the reference hard-codes, plus device options ---------------- */
+typedef struct speigen_cfg {
+  int32_t max_iter;          /* 1000   R/spEigen.R:47  */
+  int32_t n_continuation;    /* K = 10 R/spEigen.R:94  (K+1 stages) */
+  double p1;                 /* 1      R/spEigen.R:95  */
+  double pk;                 /* 7      R/spEigen.R:96  */
+  double tol_factor;         /* 1e-2   R/spEigen.R:101 */
+  double backtrack_slack;    /* 1e-9   R/spEigen.R:140 */
+  double rank_tol;           /* 1e-9   R/spEigen.R:69,79 */
+  double pd_tol;             /* -1e-10 R/spEigen.R:77 */
+  int32_t max_backtracks;    /* 200: cap on the reference's unbounded `while(1)` R/spEigen.R:126 */
+  /* initialiser (block subspace iteration replacing eigen()/svd(), R/spEigen.R:68,76) */
+  int32_t init_max_passes;   /* 300 */
+  double init_tol;           /* 2e-14: max_c ||S v_c - theta_c v_c|| <= init_tol * theta_1 */
+  int32_t init_block;        /* 0 = auto (q rounded up to the DMMA n-tile) */
+  uint64_t init_seed;
+  int32_t check_symmetric;   /* 1 */
+  int32_t check_na;          /* 1 */
+  /* devices */
+  int32_t n_gpus;            /* single-process mode: devices 0..n_gpus-1 (0 -> 1) */
+  int32_t first_device;      /* single-process mode: first CUDA ordinal */
+  int32_t fused_epilogue;    /* 1: reweighting fused into the contraction epilogue where the data flow allows */
+  int32_t verbose;
+} speigen_cfg;
+
+void speigen_cfg_default(speigen_cfg* cfg);
+
+/* ---- results ------------------------------------------------------------------------------------
+ * Caller allocates vectors / standard_vectors (m*q doubles, or 2*m*q for complex) and values (q).
+ * The trace arrays are optional (NULL to skip); the reference computes F_v but does not return it
+ * (R/spEigen.R:90,162) — it is exposed here as a side channel for parity tests. */
+typedef struct speigen_out {
+  double* vectors;             /* m x q column-major          R/spEigen.R:158-160 */
+  double* standard_vectors;    /* m x q column-major          R/spEigen.R:162 (Vx[,1:q]) */
+  double* values;              /* q                           R/spEigen.R:162 */
+  double* F;                   /* [trace_capacity] objective per outer iteration k (optional) */
+  double* step_a;              /* [trace_capacity] accepted SQUAREM step per k (optional) */
+  int32_t* backtracks_per_k;   /* [trace_capacity] (optional) */
+  int32_t* stage_of_k;         /* [trace_capacity] (optional) */
+  int32_t trace_capacity;
+  /* counters written by the library */
+  int32_t iterations;          /* k at exit */
+  int32_t backtracks;          /* total */
+  int32_t contractions;        /* streamed passes over S (or X) in the MM loop */
+  int32_t init_passes;         /* subspace-iteration passes */
+  int32_t init_converged;
+  double init_residual;        /* max_c ||S v_c - theta_c v_c|| / theta_1 at exit of the initialiser */
+  double seconds_upload;
+  double seconds_init;
+  double seconds_loop;
+} speigen_out;
+
+/* ---- one-shot drop-in calls (host pointers) — what the .Call glue binds ------------------------
+ * X: nrow x ncol column-major.  is_data == 0: covariance (nrow == ncol == m).  is_data != 0: data matrix,
+ * n = nrow samples, m = ncol variables (centred by the library, R/spEigen.R:59-60).
+ * d: q weights or NULL (default seq(1, 0.5, length.out = q), R/spEigen.R:64).  V0: m x q start or NULL. */
+int speigen_run_f64(const double* X, int64_t nrow, int64_t ncol, int is_data, double q, double rho, const double* d,
+                    const double* V0, double thres, const speigen_cfg* cfg, speigen_out* out);
+int speigen_run_c64(const double* X_interleaved, int64_t nrow, int64_t ncol, int is_data, double q, double rho,
+                    const double* d, const double* V0_interleaved, double thres, const speigen_cfg* cfg,
+                    speigen_out* out);
+
+const char* speigen_last_error(void);
+int speigen_abi_version(void);
+int speigen_device_count(void);
+
+/* ---- host-only helpers (usable without a GPU) -------------------------------------------------- */
+int speigen_validate_args(int64_t nrow, int64_t ncol, double q, double rho);      /* R/spEigen.R:52-55 */
+int speigen_default_d(int32_t q, double* d);                                      /* R/spEigen.R:64 */
+int speigen_schedule(const speigen_cfg* cfg, double* p, double* eps, double* tol);/* R/spEigen.R:94-102, K+1 each */
+int speigen_stage_constants(double p, double eps, double* c1, double* c2, double* w0); /* R/spEigen.R:110-112 */
+int speigen_shard_range(int64_t n, int32_t nparts, int32_t part, int64_t* lo, int64_t* hi);
+int32_t speigen_panel_pitch(int32_t real_columns);
+int64_t speigen_matrix_ld(int64_t contiguous_doubles);
+
+/* ---- resident solver (device-side inputs; multi-process sharding; kernel-level entry points) ----
+ * One solver per process drives the local GPU(s).  world/rank describe the row shard (covariance) or
+ * sample shard (data matrix) this process owns.  Used by bench.py, the parity tests and by the
+ * one-shot calls above. */
+typedef struct speigen_solver speigen_solver;
+
+typedef struct speigen_problem {
+  int64_t m;            /* variables */
+  int64_t n;            /* samples (data mode) ; ignored for covariance */
+  int32_t q;
+  int32_t is_complex;
+  int32_t is_data;
+  int32_t world;        /* total shards (GPUs) */
+  int32_t rank;         /* first shard owned by this process */
+  int32_t local_gpus;   /* shards owned by this process (devices first_device..) */
+} speigen_problem;
+
+int speigen_solver_create(speigen_solver** s, const speigen_problem* prob, const speigen_cfg* cfg);
+int speigen_solver_destroy(speigen_solver* s);
+/* NCCL bootstrap for multi-process runs: rank 0 makes the id, the launcher broadcasts the 128 bytes. */
+int speigen_nccl_unique_id(void* id128);
+int speigen_solver_init_comm(speigen_solver* s, const void* id128);
+/* Load the full host matrix (column-major); each local device keeps only its shard. */
+int speigen_solver_load_host(speigen_solver* s, const double* X_host);
+/* Device pointer to local shard `local_idx` in library layout, so a caller can fill it on the device:
+ * covariance: rows = owned columns of S (lo..hi), each row = one full column of S (m entries), pitch ld doubles;
+ * data: rows = variables (m), each row = owned samples (lo..hi), pitch ld doubles. */
+int speigen_solver_shard_buffer(speigen_solver* s, int32_t local_idx, double** dev_ptr, int64_t* rows,
+                                int64_t* row_len_doubles, int64_t* ld_doubles, int64_t* lo, int64_t* hi);
+/* Validation scan + centring + rho scale inputs (max diag / max column energy).  R/spEigen.R:53,59-60,72,75,82 */
+int speigen_solver_prepare(speigen_solver* s);
+/* Block subspace iteration for the top-q eigenpairs (R/spEigen.R:68-71,76-81 replacement). */
+int speigen_solver_init(speigen_solver* s, const double* V0_host_or_null, speigen_out* out);
+/* The MM loop (R/spEigen.R:105-160). */
+int speigen_solver_run(speigen_solver* s, double rho, const double* d_or_null, double thres, speigen_out* out);
+
+/* kernel-level entry points (host column-major panels in/out) */
+int speigen_solver_contract(speigen_solver* s, const double* U_host, int32_t ncols, double* Y_host);
+int speigen_solver_polar(speigen_solver* s, const double* A_host, int32_t ncols, double* U_host);
+int speigen_solver_mm_update(speigen_solver* s, const double* V_host, const double* d, const double* rho_vec,
+                             double p, double eps, int32_t fused, double* V1_host);
+int speigen_solver_objective(speigen_solver* s, const double* V_host, const double* d, const double* rho_vec,
+                             double p, double eps, double* F_out);
+int speigen_solver_eig_small(speigen_solver* s, const double* C_host, int32_t n, double* W_host, double* evals);
+/* timing: `reps` back-to-back contractions of a resident random panel, CUDA events on the launching stream,
+ * L2 flushed between repetitions when flush_l2 != 0.  ms_each[reps]. */
+int speigen_solver_time_contract(speigen_solver* s, int32_t ncols, int32_t reps, int32_t flush_l2, float* ms_each);
+int64_t speigen_solver_launch_count(speigen_solver* s);
+int speigen_solver_stream(speigen_solver* s, int32_t local_idx, void** cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEIGEN_B200_H */

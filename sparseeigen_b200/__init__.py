@@ -1,0 +1,370 @@
+"""sparseeigen_b200 — host-side mirror of sparseEigen::spEigen() over the B200 CUDA library.
+
+The reference's only interface for this path is the R closure
+    spEigen(X, q = 1, rho = 0.5, data = FALSE, d = NA, V = NA, thres = 1e-9)     (R/spEigen.R:46)
+returning list(vectors, standard_vectors, values) (R/spEigen.R:162).  R is not available in the build
+image, so this module plays the role of the R wrapper: same argument names, defaults, meaning and error
+conditions, forwarding to the C ABI in include/speigen_b200.h (libspeigen_b200.so) through ctypes.
+There is NO CPU fallback: if the CUDA library is missing or no B200 is visible the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional
+
+import numpy as np
+
+__all__ = ["spEigen", "SpEigenError", "Solver", "lib", "library_path", "default_cfg", "schedule", "default_d",
+           "shard_range", "panel_pitch"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libspeigen_b200.so"
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, _LIB_NAME)
+
+
+class SpEigenError(ValueError):
+    """Raised where the reference calls stop() (R/spEigen.R:52-55,69,75,77,79) and for device errors."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+class Cfg(C.Structure):
+    _fields_ = [
+        ("max_iter", C.c_int32), ("n_continuation", C.c_int32), ("p1", C.c_double), ("pk", C.c_double),
+        ("tol_factor", C.c_double), ("backtrack_slack", C.c_double), ("rank_tol", C.c_double), ("pd_tol", C.c_double),
+        ("max_backtracks", C.c_int32), ("init_max_passes", C.c_int32), ("init_tol", C.c_double),
+        ("init_block", C.c_int32), ("init_seed", C.c_uint64), ("check_symmetric", C.c_int32), ("check_na", C.c_int32),
+        ("n_gpus", C.c_int32), ("first_device", C.c_int32), ("fused_epilogue", C.c_int32), ("verbose", C.c_int32),
+    ]
+
+
+class Out(C.Structure):
+    _fields_ = [
+        ("vectors", C.POINTER(C.c_double)), ("standard_vectors", C.POINTER(C.c_double)), ("values", C.POINTER(C.c_double)),
+        ("F", C.POINTER(C.c_double)), ("step_a", C.POINTER(C.c_double)), ("backtracks_per_k", C.POINTER(C.c_int32)),
+        ("stage_of_k", C.POINTER(C.c_int32)), ("trace_capacity", C.c_int32),
+        ("iterations", C.c_int32), ("backtracks", C.c_int32), ("contractions", C.c_int32), ("init_passes", C.c_int32),
+        ("init_converged", C.c_int32), ("init_residual", C.c_double), ("seconds_upload", C.c_double),
+        ("seconds_init", C.c_double), ("seconds_loop", C.c_double),
+    ]
+
+
+class Problem(C.Structure):
+    _fields_ = [("m", C.c_int64), ("n", C.c_int64), ("q", C.c_int32), ("is_complex", C.c_int32), ("is_data", C.c_int32),
+                ("world", C.c_int32), ("rank", C.c_int32), ("local_gpus", C.c_int32)]
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+
+
+def lib():
+    """Load libspeigen_b200.so (fails loudly: the product path has no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          f"or `make -C sparseeigen_b200/csrc`; there is no CPU fallback")
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    L.speigen_last_error.restype = C.c_char_p
+    L.speigen_cfg_default.argtypes = [C.POINTER(Cfg)]
+    L.speigen_run_f64.argtypes = [_dp, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, _dp, _dp, C.c_double,
+                                  C.POINTER(Cfg), C.POINTER(Out)]
+    L.speigen_run_c64.argtypes = L.speigen_run_f64.argtypes
+    L.speigen_validate_args.argtypes = [C.c_int64, C.c_int64, C.c_double, C.c_double]
+    L.speigen_default_d.argtypes = [C.c_int32, _dp]
+    L.speigen_schedule.argtypes = [C.POINTER(Cfg), _dp, _dp, _dp]
+    L.speigen_stage_constants.argtypes = [C.c_double, C.c_double, _dp, _dp, _dp]
+    L.speigen_shard_range.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.speigen_panel_pitch.argtypes = [C.c_int32]
+    L.speigen_panel_pitch.restype = C.c_int32
+    L.speigen_matrix_ld.argtypes = [C.c_int64]
+    L.speigen_matrix_ld.restype = C.c_int64
+    L.speigen_solver_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Problem), C.POINTER(Cfg)]
+    L.speigen_solver_destroy.argtypes = [C.c_void_p]
+    L.speigen_nccl_unique_id.argtypes = [C.c_void_p]
+    L.speigen_solver_init_comm.argtypes = [C.c_void_p, C.c_void_p]
+    L.speigen_solver_load_host.argtypes = [C.c_void_p, _dp]
+    L.speigen_solver_shard_buffer.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)] + [C.POINTER(C.c_int64)] * 5
+    L.speigen_solver_prepare.argtypes = [C.c_void_p]
+    L.speigen_solver_init.argtypes = [C.c_void_p, _dp, C.POINTER(Out)]
+    L.speigen_solver_run.argtypes = [C.c_void_p, C.c_double, _dp, C.c_double, C.POINTER(Out)]
+    L.speigen_solver_contract.argtypes = [C.c_void_p, _dp, C.c_int32, _dp]
+    L.speigen_solver_polar.argtypes = [C.c_void_p, _dp, C.c_int32, _dp]
+    L.speigen_solver_mm_update.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int32, _dp]
+    L.speigen_solver_objective.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
+    L.speigen_solver_eig_small.argtypes = [C.c_void_p, _dp, C.c_int32, _dp, _dp]
+    L.speigen_solver_time_contract.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
+    L.speigen_solver_launch_count.argtypes = [C.c_void_p]
+    L.speigen_solver_launch_count.restype = C.c_int64
+    L.speigen_solver_stream.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise SpEigenError(rc, lib().speigen_last_error().decode("utf-8", "replace"))
+
+
+def default_cfg(**overrides) -> Cfg:
+    cfg = Cfg()
+    lib().speigen_cfg_default(C.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise TypeError(f"unknown cfg field {k}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+def schedule(cfg: Optional[Cfg] = None):
+    """(p, eps, tol) of R/spEigen.R:94-102."""
+    cfg = cfg or default_cfg()
+    n = cfg.n_continuation + 1
+    p, e, t = (np.empty(n) for _ in range(3))
+    _check(lib().speigen_schedule(C.byref(cfg), _ptr(p), _ptr(e), _ptr(t)))
+    return p, e, t
+
+
+def default_d(q: int) -> np.ndarray:
+    d = np.empty(q)
+    _check(lib().speigen_default_d(q, _ptr(d)))
+    return d
+
+
+def shard_range(n: int, nparts: int, part: int):
+    lo, hi = C.c_int64(), C.c_int64()
+    _check(lib().speigen_shard_range(n, nparts, part, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def panel_pitch(ncols_real: int) -> int:
+    return lib().speigen_panel_pitch(ncols_real)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    return a.ctypes.data_as(_dp)
+
+
+def _as_colmajor(X: np.ndarray, cplx: bool) -> np.ndarray:
+    """Column-major float64 / complex128 buffer exactly as R stores a matrix."""
+    return np.asfortranarray(X, dtype=np.complex128 if cplx else np.float64)
+
+
+def _is_na(v) -> bool:
+    if v is None:
+        return True
+    try:
+        return bool(np.isnan(v))
+    except TypeError:
+        return False
+
+
+class _OutBuffers:
+    def __init__(self, m, q, cplx, trace_capacity=1000):
+        dt = np.complex128 if cplx else np.float64
+        self.vectors = np.zeros((m, q), dtype=dt, order="F")
+        self.standard_vectors = np.zeros((m, q), dtype=dt, order="F")
+        self.values = np.zeros(q)
+        self.F = np.zeros(trace_capacity)
+        self.step_a = np.zeros(trace_capacity)
+        self.bt = np.zeros(trace_capacity, dtype=np.int32)
+        self.stage = np.zeros(trace_capacity, dtype=np.int32)
+        o = Out()
+        o.vectors = self.vectors.ctypes.data_as(_dp)
+        o.standard_vectors = self.standard_vectors.ctypes.data_as(_dp)
+        o.values = _ptr(self.values)
+        o.F = _ptr(self.F)
+        o.step_a = _ptr(self.step_a)
+        o.backtracks_per_k = self.bt.ctypes.data_as(C.POINTER(C.c_int32))
+        o.stage_of_k = self.stage.ctypes.data_as(C.POINTER(C.c_int32))
+        o.trace_capacity = trace_capacity
+        self.c = o
+
+    def result(self):
+        k = min(self.c.iterations, len(self.F))
+        info = dict(iterations=self.c.iterations, backtracks=self.c.backtracks, contractions=self.c.contractions,
+                    init_passes=self.c.init_passes, init_converged=bool(self.c.init_converged),
+                    init_residual=self.c.init_residual, seconds_upload=self.c.seconds_upload,
+                    seconds_init=self.c.seconds_init, seconds_loop=self.c.seconds_loop,
+                    F=self.F[:k].copy(), step_a=self.step_a[:k].copy(), backtracks_per_k=self.bt[:k].copy(),
+                    stage_of_k=self.stage[:k].copy())
+        return dict(vectors=self.vectors, standard_vectors=self.standard_vectors, values=self.values, info=info)
+
+
+def spEigen(X, q=1, rho=0.5, data=False, d=None, V=None, thres=1e-9, *, n_gpus=1, cfg: Optional[Cfg] = None,
+            **cfg_overrides):
+    """Sparse (orthogonal) eigenvectors of a covariance or data matrix — drop-in for R/spEigen.R:46.
+
+    Returns dict(vectors, standard_vectors, values) as the reference's list (R/spEigen.R:162) plus an
+    'info' side channel (objective trajectory F_v, which the reference computes but does not return).
+    `d=None` / `V=None` play the role of R's NA defaults."""
+    X = np.asarray(X)
+    if X.ndim == 1:                      # as.matrix(<vector>) is n x 1   (R/spEigen.R:50)
+        X = X.reshape(-1, 1)
+    if X.ndim != 2:
+        raise SpEigenError(23, "X must be a matrix")
+    nrow, m = X.shape
+    if m == 1:
+        raise SpEigenError(1, "Data is univariate!")                                   # :52
+    if _is_na(q) or _is_na(rho) or np.isnan(X).any():
+        raise SpEigenError(2, "This function cannot handle NAs.")                      # :53
+    L = lib()
+    _check(L.speigen_validate_args(nrow, m, float(q), float(rho)))                     # :54-55
+    q = int(q)
+    cplx = np.iscomplexobj(X)
+    Xf = _as_colmajor(X, cplx)
+    cfg = cfg or default_cfg()
+    cfg.n_gpus = n_gpus
+    for k, v in cfg_overrides.items():
+        if not hasattr(cfg, k):
+            raise TypeError(f"unknown cfg field {k}")
+        setattr(cfg, k, v)
+    dd = None if d is None else np.ascontiguousarray(d, dtype=np.float64)
+    if dd is not None and dd.size != q:
+        raise SpEigenError(23, "d must have length q")
+    VV = None
+    if V is not None:
+        VV = _as_colmajor(np.asarray(V), cplx)
+        if VV.shape != (m, q):
+            raise SpEigenError(23, "V must be m x q")
+    ob = _OutBuffers(m, q, cplx, trace_capacity=max(cfg.max_iter, 1))
+    fn = L.speigen_run_c64 if cplx else L.speigen_run_f64
+    rc = fn(Xf.ctypes.data_as(_dp), nrow, m, 1 if data else 0, float(q), float(rho), _ptr(dd),
+            None if VV is None else VV.ctypes.data_as(_dp), float(thres), C.byref(cfg), C.byref(ob.c))
+    _check(rc)
+    return ob.result()
+
+
+class Solver:
+    """Resident solver handle (speigen_solver_* of the C ABI): kernel-level entry points for the parity
+    tests and the device-resident benchmark path."""
+
+    def __init__(self, m, q, *, n=0, is_complex=False, is_data=False, world=1, rank=0, local_gpus=1,
+                 cfg: Optional[Cfg] = None, **cfg_overrides):
+        self.L = lib()
+        self.cfg = cfg or default_cfg(**cfg_overrides)
+        self.m, self.n, self.q = int(m), int(n), int(q)
+        self.cplx, self.data = bool(is_complex), bool(is_data)
+        self.prob = Problem(m=self.m, n=self.n, q=self.q, is_complex=int(self.cplx), is_data=int(self.data), world=world,
+                            rank=rank, local_gpus=local_gpus)
+        self.h = C.c_void_p()
+        _check(self.L.speigen_solver_create(C.byref(self.h), C.byref(self.prob), C.byref(self.cfg)))
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.L.speigen_solver_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def dtype(self):
+        return np.complex128 if self.cplx else np.float64
+
+    def init_comm(self, unique_id: Optional[bytes] = None):
+        if unique_id is None:
+            _check(self.L.speigen_solver_init_comm(self.h, None))
+        else:
+            buf = C.create_string_buffer(unique_id, 128)
+            _check(self.L.speigen_solver_init_comm(self.h, buf))
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().speigen_nccl_unique_id(buf))
+        return buf.raw
+
+    def load(self, X):
+        Xf = _as_colmajor(np.asarray(X), self.cplx)
+        _check(self.L.speigen_solver_load_host(self.h, Xf.ctypes.data_as(_dp)))
+
+    def shard_buffer(self, local_idx=0):
+        p = C.c_void_p()
+        v = [C.c_int64() for _ in range(5)]
+        _check(self.L.speigen_solver_shard_buffer(self.h, local_idx, C.byref(p), *[C.byref(x) for x in v]))
+        return dict(ptr=p.value, rows=v[0].value, row_len=v[1].value, ld=v[2].value, lo=v[3].value, hi=v[4].value)
+
+    def prepare(self):
+        _check(self.L.speigen_solver_prepare(self.h))
+
+    def init(self, V0=None):
+        ob = _OutBuffers(self.m, self.q, self.cplx, 1)
+        VV = None if V0 is None else _as_colmajor(np.asarray(V0), self.cplx)
+        _check(self.L.speigen_solver_init(self.h, None if VV is None else VV.ctypes.data_as(_dp), C.byref(ob.c)))
+        return dict(init_passes=ob.c.init_passes, init_converged=bool(ob.c.init_converged),
+                    init_residual=ob.c.init_residual, seconds_init=ob.c.seconds_init)
+
+    def run(self, rho=0.5, d=None, thres=1e-9):
+        ob = _OutBuffers(self.m, self.q, self.cplx, max(self.cfg.max_iter, 1))
+        dd = None if d is None else np.ascontiguousarray(d, dtype=np.float64)
+        _check(self.L.speigen_solver_run(self.h, float(rho), _ptr(dd), float(thres), C.byref(ob.c)))
+        return ob.result()
+
+    def contract(self, U):
+        U = _as_colmajor(np.asarray(U), self.cplx)
+        Y = np.zeros_like(U, order="F")
+        _check(self.L.speigen_solver_contract(self.h, U.ctypes.data_as(_dp), U.shape[1], Y.ctypes.data_as(_dp)))
+        return Y
+
+    def polar(self, A):
+        A = _as_colmajor(np.asarray(A), self.cplx)
+        U = np.zeros_like(A, order="F")
+        _check(self.L.speigen_solver_polar(self.h, A.ctypes.data_as(_dp), A.shape[1], U.ctypes.data_as(_dp)))
+        return U
+
+    def mm_update(self, V, d, rho_vec, p, eps, fused=True):
+        V = _as_colmajor(np.asarray(V), self.cplx)
+        V1 = np.zeros_like(V, order="F")
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        r = np.ascontiguousarray(rho_vec, dtype=np.float64)
+        _check(self.L.speigen_solver_mm_update(self.h, V.ctypes.data_as(_dp), _ptr(d), _ptr(r), float(p), float(eps),
+                                               1 if fused else 0, V1.ctypes.data_as(_dp)))
+        return V1
+
+    def objective(self, V, d, rho_vec, p, eps) -> float:
+        V = _as_colmajor(np.asarray(V), self.cplx)
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        r = np.ascontiguousarray(rho_vec, dtype=np.float64)
+        F = C.c_double()
+        _check(self.L.speigen_solver_objective(self.h, V.ctypes.data_as(_dp), _ptr(d), _ptr(r), float(p), float(eps),
+                                               C.byref(F)))
+        return F.value
+
+    def eig_small(self, Cm):
+        Cm = _as_colmajor(np.asarray(Cm), self.cplx)
+        n = Cm.shape[0]
+        W = np.zeros_like(Cm, order="F")
+        ev = np.zeros(n)
+        _check(self.L.speigen_solver_eig_small(self.h, Cm.ctypes.data_as(_dp), n, W.ctypes.data_as(_dp), _ptr(ev)))
+        return ev, W
+
+    def time_contract(self, ncols, reps, flush_l2=True):
+        ms = (C.c_float * reps)()
+        _check(self.L.speigen_solver_time_contract(self.h, ncols, reps, 1 if flush_l2 else 0, ms))
+        return np.array(ms[:], dtype=np.float64)
+
+    def launch_count(self) -> int:
+        return int(self.L.speigen_solver_launch_count(self.h))

@@ -1,0 +1,309 @@
+// extern "C" surface of libspeigen_b200.so (declared in include/speigen_b200.h).
+#include "solver.cuh"
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace speigen {
+const char* last_error();
+long long launch_count();
+}  // namespace speigen
+using namespace speigen;
+
+#define API_TRY(x)                       \
+  do {                                   \
+    int rc__ = (x);                      \
+    if (rc__ != SPEIGEN_OK) return rc__; \
+  } while (0)
+
+static double wall_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" {
+
+void speigen_cfg_default(speigen_cfg* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->max_iter = 1000;
+  c->n_continuation = 10;
+  c->p1 = 1.0;
+  c->pk = 7.0;
+  c->tol_factor = 1e-2;
+  c->backtrack_slack = 1e-9;
+  c->rank_tol = 1e-9;
+  c->pd_tol = -1e-10;
+  c->max_backtracks = 200;
+  c->init_max_passes = 300;
+  c->init_tol = 2e-14;
+  c->init_block = 0;
+  c->init_seed = 42;
+  c->check_symmetric = 1;
+  c->check_na = 1;
+  c->n_gpus = 1;
+  c->first_device = 0;
+  c->fused_epilogue = 1;
+  c->verbose = 0;
+}
+
+const char* speigen_last_error(void) { return last_error(); }
+int speigen_abi_version(void) { return SPEIGEN_ABI_VERSION; }
+int speigen_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// R/spEigen.R:52-55 (anyNA(X) is checked on the device during solver_prepare)
+int speigen_validate_args(int64_t nrow, int64_t ncol, double q, double rho) {
+  (void)nrow;
+  if (ncol == 1) { set_error("Data is univariate!"); return SPEIGEN_ERR_UNIVARIATE; }
+  if (ncol < 1) { set_error("X must be a matrix"); return SPEIGEN_ERR_ARG; }
+  if (std::isnan(q) || std::isnan(rho)) { set_error("This function cannot handle NAs."); return SPEIGEN_ERR_NA; }
+  if (std::fmod(q, 1.0) != 0.0 || q <= 0) { set_error("The input argument q should be a positive integer."); return SPEIGEN_ERR_Q; }
+  if (rho <= 0) { set_error("The input argument rho should be positive."); return SPEIGEN_ERR_RHO; }
+  return SPEIGEN_OK;
+}
+
+// seq(from = 1, to = 0.5, length.out = q)   R/spEigen.R:64
+int speigen_default_d(int32_t q, double* d) {
+  if (q < 1 || !d) return SPEIGEN_ERR_ARG;
+  if (q == 1) { d[0] = 1.0; return SPEIGEN_OK; }
+  for (int i = 0; i < q; ++i) d[i] = 1.0 - 0.5 * static_cast<double>(i) / static_cast<double>(q - 1);
+  return SPEIGEN_OK;
+}
+
+// pp <- 10^-(p1 * (pk/p1)^((0:K)/K)); tol <- pp * 1e-2; Eps <- pp    R/spEigen.R:94-102
+int speigen_schedule(const speigen_cfg* cfg, double* p, double* eps, double* tol) {
+  speigen_cfg def;
+  if (!cfg) { speigen_cfg_default(&def); cfg = &def; }
+  const int K = cfg->n_continuation;
+  const double gamma = std::pow(cfg->pk / cfg->p1, 1.0 / K);
+  for (int i = 0; i <= K; ++i) {
+    const double e = cfg->p1 * std::pow(gamma, static_cast<double>(i));
+    const double pp = std::pow(10.0, -e);
+    if (p) p[i] = pp;
+    if (eps) eps[i] = pp;
+    if (tol) tol[i] = pp * cfg->tol_factor;
+  }
+  return SPEIGEN_OK;
+}
+
+int speigen_stage_constants(double p, double eps, double* c1, double* c2, double* w0) {
+  const StageConsts s = make_stage(p, eps);
+  if (c1) *c1 = s.c1;
+  if (c2) *c2 = s.c2;
+  if (w0) *w0 = s.w0;
+  return SPEIGEN_OK;
+}
+
+int speigen_shard_range(int64_t n, int32_t nparts, int32_t part, int64_t* lo, int64_t* hi) {
+  if (nparts < 1 || part < 0 || part >= nparts || n < 0) return SPEIGEN_ERR_ARG;
+  const int64_t per = (n + nparts - 1) / nparts;
+  const int64_t l = std::min<int64_t>(n, per * part);
+  if (lo) *lo = l;
+  if (hi) *hi = std::min<int64_t>(n, l + per);
+  return SPEIGEN_OK;
+}
+int32_t speigen_panel_pitch(int32_t real_columns) { return panel_pitch(real_columns); }
+int64_t speigen_matrix_ld(int64_t contiguous_doubles) { return (contiguous_doubles + 15) / 16 * 16; }
+
+// ---- resident solver --------------------------------------------------------------------------
+int speigen_solver_create(speigen_solver** s, const speigen_problem* prob, const speigen_cfg* cfg) {
+  if (!s || !prob) return SPEIGEN_ERR_ARG;
+  speigen_cfg def;
+  if (!cfg) { speigen_cfg_default(&def); cfg = &def; }
+  speigen_solver* h = new (std::nothrow) speigen_solver();
+  if (!h) return SPEIGEN_ERR_NOMEM;
+  const int rc = h->impl.create(prob, cfg);
+  if (rc != SPEIGEN_OK) { h->impl.destroy(); delete h; *s = nullptr; return rc; }
+  *s = h;
+  return SPEIGEN_OK;
+}
+int speigen_solver_destroy(speigen_solver* s) {
+  if (!s) return SPEIGEN_OK;
+  s->impl.destroy();
+  delete s;
+  return SPEIGEN_OK;
+}
+int speigen_nccl_unique_id(void* id128) {
+  const NcclApi* nc = nccl_api();
+  if (!nc) return SPEIGEN_ERR_NCCL;
+  ncclUniqueId id;
+  const int r = nc->GetUniqueId(&id);
+  if (r != NCCL_SUCCESS) { set_error("ncclGetUniqueId failed: %s", nc->GetErrorString(r)); return SPEIGEN_ERR_NCCL; }
+  std::memcpy(id128, &id, sizeof(id));
+  return SPEIGEN_OK;
+}
+int speigen_solver_init_comm(speigen_solver* s, const void* id128) {
+  if (!s) return SPEIGEN_ERR_ARG;
+  return id128 ? s->impl.init_comm_rank(id128) : s->impl.init_comm_all();
+}
+int speigen_solver_load_host(speigen_solver* s, const double* X) { return s->impl.load_host(X); }
+int speigen_solver_shard_buffer(speigen_solver* s, int32_t li, double** dev_ptr, int64_t* rows, int64_t* row_len,
+                                int64_t* ld, int64_t* lo, int64_t* hi) {
+  if (!s || li < 0 || li >= static_cast<int>(s->impl.devs.size())) return SPEIGEN_ERR_ARG;
+  Dev& d = s->impl.devs[li];
+  if (dev_ptr) *dev_ptr = d.A;
+  if (rows) *rows = d.a_rows;
+  if (row_len) *row_len = d.a_kd;
+  if (ld) *ld = d.a_ld;
+  if (lo) *lo = d.lo;
+  if (hi) *hi = d.hi;
+  s->impl.loaded = true;
+  return SPEIGEN_OK;
+}
+int speigen_solver_prepare(speigen_solver* s) { return s->impl.prepare(); }
+int speigen_solver_init(speigen_solver* s, const double* V0, speigen_out* out) { return s->impl.init_vectors(V0, out); }
+int speigen_solver_run(speigen_solver* s, double rho, const double* d, double thres, speigen_out* out) {
+  if (std::isnan(rho)) { set_error("This function cannot handle NAs."); return SPEIGEN_ERR_NA; }
+  if (rho <= 0) { set_error("The input argument rho should be positive."); return SPEIGEN_ERR_RHO; }
+  return s->impl.run(rho, d, thres, out);
+}
+int64_t speigen_solver_launch_count(speigen_solver*) { return launch_count(); }
+int speigen_solver_stream(speigen_solver* s, int32_t li, void** st) {
+  if (!s || li < 0 || li >= static_cast<int>(s->impl.devs.size())) return SPEIGEN_ERR_ARG;
+  *st = s->impl.devs[li].st;
+  return SPEIGEN_OK;
+}
+
+// ---- kernel-level entry points ----------------------------------------------------------------
+static int ensure_maps(Solver& S) {
+  if (!S.devs[0].Astd.ptr) return S.build_tensor_maps();
+  return SPEIGEN_OK;
+}
+
+int speigen_solver_contract(speigen_solver* s, const double* U_host, int32_t ncols, double* Y_host) {
+  Solver& S = s->impl;
+  if (ncols < 1 || ncols > S.bq) { set_error("contract: ncols %d outside 1..%d", ncols, S.bq); return SPEIGEN_ERR_ARG; }
+  API_TRY(ensure_maps(S));
+  const PanelDims pd = make_dims(S.m, ncols, S.cplx);
+  API_TRY(S.op_upload_panel(U_host, BQ, pd));
+  API_TRY(S.op_contract(BQ, pd, BZ, NBUF, NBUF, false, make_stage(0.1, 0.1)));
+  return S.op_download_panel(BZ, pd, Y_host);
+}
+
+int speigen_solver_polar(speigen_solver* s, const double* A_host, int32_t ncols, double* U_host) {
+  Solver& S = s->impl;
+  if (ncols < 1 || ncols > S.bq) { set_error("polar: ncols %d outside 1..%d", ncols, S.bq); return SPEIGEN_ERR_ARG; }
+  const PanelDims pd = make_dims(S.m, ncols, S.cplx);
+  API_TRY(S.op_upload_panel(A_host, BQ, pd));
+  API_TRY(S.op_polar(BQ, BZ, pd, false, nullptr, 0));
+  return S.op_download_panel(BZ, pd, U_host);
+}
+
+int speigen_solver_mm_update(speigen_solver* s, const double* V_host, const double* d, const double* rho_vec, double p,
+                             double eps, int32_t fused, double* V1_host) {
+  Solver& S = s->impl;
+  API_TRY(ensure_maps(S));
+  const PanelDims pd = S.pdq;
+  const StageConsts sc = make_stage(p, eps);
+  API_TRY(S.op_upload_panel(V_host, BV, pd));
+  API_TRY(S.set_qvecs(d, rho_vec));
+  for (Dev& dv : S.devs) {
+    cudaSetDevice(dv.ordinal);
+    API_TRY(launch_absmin(pd, dv.buf[BV], dv.absmin_a, dv.st));
+    API_TRY(launch_wmax(pd, dv.absmin_a, sc, dv.wmax, dv.st));
+  }
+  if (fused) {
+    API_TRY(S.op_contract(BV, pd, NBUF, BB, BV, false, sc));
+    API_TRY(S.op_polar(BB, BV1, pd, false, nullptr, 0));
+  } else {
+    API_TRY(S.op_contract(BV, pd, BY, NBUF, NBUF, false, sc));
+    for (Dev& dv : S.devs) {
+      cudaSetDevice(dv.ordinal);
+      API_TRY(launch_reweight(pd, dv.buf[BY], dv.buf[BV], dv.dvec, dv.rho, dv.wmax, sc, dv.buf[BB], dv.ps.gram_part, dv.st));
+    }
+    API_TRY(S.op_polar(BB, BV1, pd, true, nullptr, 0));
+  }
+  return S.op_download_panel(BV1, pd, V1_host);
+}
+
+int speigen_solver_objective(speigen_solver* s, const double* V_host, const double* d, const double* rho_vec, double p,
+                             double eps, double* F_out) {
+  Solver& S = s->impl;
+  API_TRY(ensure_maps(S));
+  const PanelDims pd = S.pdq;
+  const StageConsts sc = make_stage(p, eps);
+  API_TRY(S.op_upload_panel(V_host, BV0, pd));
+  API_TRY(S.set_qvecs(d, rho_vec));
+  API_TRY(S.op_contract(BV0, pd, BY0, NBUF, BV0, true, sc));
+  for (Dev& dv : S.devs) {
+    cudaSetDevice(dv.ordinal);
+    API_TRY(launch_objective(pd, dv.buf[BV0], sc, dv.dots_part, S.n_dot_parts, dv.dvec, dv.rho, dv.ps, dv.scal + 8, dv.st));
+  }
+  API_TRY(S.read_scalars(9 + 2 * pd.q));
+  *F_out = S.h_scal[8];
+  return SPEIGEN_OK;
+}
+
+int speigen_solver_eig_small(speigen_solver* s, const double* C_host, int32_t nn, double* W_host, double* evals) {
+  Solver& S = s->impl;
+  if (nn < 1 || nn > S.bq) { set_error("eig_small: n %d outside 1..%d", nn, S.bq); return SPEIGEN_ERR_ARG; }
+  const int e = 1 + S.cplx;
+  const PanelDims pd = make_dims(S.m, nn, S.cplx);
+  std::vector<double> rm(static_cast<size_t>(nn) * nn * e), wm(static_cast<size_t>(nn) * nn * e);
+  for (int a = 0; a < nn; ++a)
+    for (int b = 0; b < nn; ++b)
+      for (int k = 0; k < e; ++k) rm[(static_cast<size_t>(a) * nn + b) * e + k] = C_host[(static_cast<size_t>(b) * nn + a) * e + k];
+  Dev& d = S.devs[0];
+  cudaSetDevice(d.ordinal);
+  SPE_CUDA(cudaMemcpyAsync(d.ps.gram_part, rm.data(), rm.size() * sizeof(double), cudaMemcpyHostToDevice, d.st));
+  API_TRY(launch_small(pd, d.ps.gram_part, 1, SMALL_EIGVECS, d.Msmall, d.evals, d.status, d.st));
+  SPE_CUDA(cudaMemcpyAsync(wm.data(), d.Msmall, wm.size() * sizeof(double), cudaMemcpyDeviceToHost, d.st));
+  SPE_CUDA(cudaMemcpyAsync(evals, d.evals, nn * sizeof(double), cudaMemcpyDeviceToHost, d.st));
+  SPE_CUDA(cudaStreamSynchronize(d.st));
+  for (int a = 0; a < nn; ++a)
+    for (int b = 0; b < nn; ++b)
+      for (int k = 0; k < e; ++k) W_host[(static_cast<size_t>(b) * nn + a) * e + k] = wm[(static_cast<size_t>(a) * nn + b) * e + k];
+  return SPEIGEN_OK;
+}
+
+int speigen_solver_time_contract(speigen_solver* s, int32_t ncols, int32_t reps, int32_t flush_l2, float* ms_each) {
+  Solver& S = s->impl;
+  API_TRY(ensure_maps(S));
+  return S.time_contract(ncols, reps, flush_l2, ms_each);
+}
+
+// ---- one-shot drop-in calls -------------------------------------------------------------------
+static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data, int is_complex, double q, double rho,
+                       const double* d, const double* V0, double thres, const speigen_cfg* cfg_in, speigen_out* out) {
+  if (!X || !out) { set_error("null argument"); return SPEIGEN_ERR_ARG; }
+  speigen_cfg cfg;
+  if (cfg_in) cfg = *cfg_in; else speigen_cfg_default(&cfg);
+  API_TRY(speigen_validate_args(nrow, ncol, q, rho));
+  if (!is_data && nrow != ncol) { set_error("The covariance matrix is not symmetric."); return SPEIGEN_ERR_NOT_SYMMETRIC; }
+  speigen_problem pb;
+  std::memset(&pb, 0, sizeof(pb));
+  pb.m = ncol;
+  pb.n = nrow;
+  pb.q = static_cast<int32_t>(q);
+  pb.is_complex = is_complex;
+  pb.is_data = is_data ? 1 : 0;
+  pb.world = cfg.n_gpus > 0 ? cfg.n_gpus : 1;
+  pb.rank = 0;
+  pb.local_gpus = pb.world;
+  speigen_solver* s = nullptr;
+  API_TRY(speigen_solver_create(&s, &pb, &cfg));
+  int rc = s->impl.init_comm_all();
+  const double t0 = wall_s();
+  if (rc == SPEIGEN_OK) rc = s->impl.load_host(X);
+  out->seconds_upload = wall_s() - t0;
+  if (rc == SPEIGEN_OK) rc = s->impl.prepare();
+  if (rc == SPEIGEN_OK) rc = s->impl.init_vectors(V0, out);
+  if (rc == SPEIGEN_OK) rc = s->impl.run(rho, d, thres, out);
+  speigen_solver_destroy(s);
+  return rc;
+}
+
+int speigen_run_f64(const double* X, int64_t nrow, int64_t ncol, int is_data, double q, double rho, const double* d,
+                    const double* V0, double thres, const speigen_cfg* cfg, speigen_out* out) {
+  return run_oneshot(X, nrow, ncol, is_data, 0, q, rho, d, V0, thres, cfg, out);
+}
+int speigen_run_c64(const double* X, int64_t nrow, int64_t ncol, int is_data, double q, double rho, const double* d,
+                    const double* V0, double thres, const speigen_cfg* cfg, speigen_out* out) {
+  return run_oneshot(X, nrow, ncol, is_data, 1, q, rho, d, V0, thres, cfg, out);
+}
+
+}  // extern "C"

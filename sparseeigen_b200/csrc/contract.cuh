@@ -1,0 +1,67 @@
+// K1: the tall-skinny contraction  Y = A * P  (and its transposed form  T = A^T * P)  where A is the
+// streamed matrix (covariance slab / data shard, the HBM-bound operand) and P is an m x q panel.
+// Replaces the two dgemm/zgemm calls of R/spEigen.R:177 and the X %*% V0 products of :136,:138.
+#pragma once
+#include "common.cuh"
+
+namespace speigen {
+
+// Streamed matrix resident in HBM, viewed as a row-major real matrix of `rows` x `kd` doubles with
+// row pitch `ld` doubles (ld % 16 == 0, base 128-byte aligned).  R's column-major S (m x m) is
+// exactly this with rows = columns of S (S = S^H); complex entries are interleaved
+// {re,im} so kd = 2 * (complex length).
+struct StreamMat {
+  const double* ptr = nullptr;
+  int64_t rows = 0;   // number of rows (outputs of the standard form)
+  int64_t kd = 0;     // contiguous (contracted) dimension in doubles
+  int64_t ld = 0;     // row pitch in doubles
+  CUtensorMap tmap;   // box = 16 doubles x TJ rows, SWIZZLE_128B
+  int box_rows = 0;
+};
+
+// Epilogue selector/arguments for the standard form.
+struct EpiArgs {
+  double* Y = nullptr;             // raw product rows -> Y[(row_off + j) * pitch + c]
+  double* B = nullptr;             // fused reweighting: B = d*Y - (w(|V|) - wmax) * V * rho   (R/spEigen.R:170-177)
+  const double* V = nullptr;       // panel the weights / column dots are taken from (global rows)
+  const double* d = nullptr;       // [q]
+  const double* rho = nullptr;     // [q]
+  const double* wmax = nullptr;    // [q] column max of the weights (R/spEigen.R:176 apply(...,2,max))
+  double* dots = nullptr;          // per-row-tile partial column dots Re(conj(V) .* Y): [n_row_tiles][q]
+  StageConsts sc{};
+  int q = 0;
+  int cplx = 0;
+  int pitch = 0;                   // panel pitch (doubles)
+  int64_t row_off = 0;             // global row of local output row 0 (row-sharded covariance)
+};
+
+struct ContractWorkspace {
+  double* partials = nullptr;      // split-K partial tiles
+  int* counters = nullptr;         // per row tile arrival counters (self-resetting)
+  size_t partial_slots = 0;
+  int n_counters = 0;
+};
+
+// Tile configuration of the standard form.
+constexpr int kTJ = 256;           // output rows per CTA tile
+constexpr int kNBox = 2;           // TMA boxes (16 doubles wide) per pipeline stage
+constexpr int kTK = 16 * kNBox;    // contracted doubles per stage
+constexpr int kConsumerWarps = 8;
+constexpr int kMT = kTJ / (8 * kConsumerWarps);   // m-tiles (8 rows) per warp = 4
+constexpr int kThreads = kConsumerWarps * 32 + 32;
+
+int make_stream_mat(StreamMat* sm, const double* ptr, int64_t rows, int64_t kd, int64_t ld, int box_rows);
+
+// Y(rows x ncr) = A(rows x kd) * P(kd x ncr).  P is a panel with pitch panel_pitch(ncr) whose row count
+// is padded (with zeros) to a multiple of kTK.  Deterministic (fixed-order split-K fix-up).
+int launch_contract_std(const StreamMat& A, const double* P, int ncr, const EpiArgs& epi,
+                        const ContractWorkspace& ws, int num_sms, cudaStream_t stream);
+size_t contract_workspace_slots(int64_t rows, int num_sms);
+size_t contract_slot_doubles(int ncr);
+
+// T(kd x ncr) = A^T * P(rows x ncr)   (data-matrix mode first product, R/spEigen.R:136 `X %*% V0`).
+int launch_contract_tr(const StreamMat& A, const double* P, int ncr, double* T, int t_pitch,
+                       const ContractWorkspace& ws, int num_sms, cudaStream_t stream);
+size_t contract_tr_workspace_slots(int64_t kd, int num_sms);
+
+}  // namespace speigen

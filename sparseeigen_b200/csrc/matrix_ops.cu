@@ -1,0 +1,184 @@
+#include "matrix_ops.cuh"
+#include "../../include/speigen_b200.h"
+#include <cfloat>
+
+namespace speigen {
+void note_launch(int n);
+namespace {
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 32 x 32 element tiles, 32 x 8 threads.  E = doubles per element.
+template <int E>
+__global__ void __launch_bounds__(256) k_scan_cov(const double* A, int64_t rows, int64_t m, int64_t ld, int64_t lo,
+                                                  int full_check, double* part, int* ticket, double* out4) {
+  __shared__ double tileT[32][32 * E + 1];
+  __shared__ double s_red[4][8];
+  __shared__ int s_is_last;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t tr = (rows + 31) / 32, tc = (m + 31) / 32;
+  const int64_t ntiles = tr * tc;
+  double sdiff = 0.0, sabs = 0.0, dmax = -DBL_MAX, nnan = 0.0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t tj = t / tc, ti = t - tj * tc;
+    if (full_check) {
+      // transposed tile: rows ti*32.., columns tj*32..
+      for (int r = ty; r < 32; r += 8) {
+        const int64_t jj = ti * 32 + r, ii = tj * 32 + tx;
+#pragma unroll
+        for (int e = 0; e < E; ++e) tileT[r][tx * E + e] = (jj < rows && ii < m) ? A[jj * ld + ii * E + e] : 0.0;
+      }
+      __syncthreads();
+    }
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t j = tj * 32 + r, i = ti * 32 + tx;
+      if (j < rows && i < m) {
+        double a[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) a[e] = A[j * ld + i * E + e];
+        const double ab = (E == 2) ? hypot(a[0], a[E - 1]) : fabs(a[0]);
+        if (isnan(ab)) nnan += 1.0;
+        sabs += ab;
+        if (full_check) {
+          // S[i][j] element lives at tileT[tx][r]; compare with conj
+          const double br = tileT[tx][r * E], bi = (E == 2) ? -tileT[tx][r * E + E - 1] : 0.0;
+          sdiff += (E == 2) ? hypot(a[0] - br, a[E - 1] - bi) : fabs(a[0] - br);
+        }
+        if (i == lo + j) dmax = fmax(dmax, a[0]);
+      }
+    }
+    if (full_check) __syncthreads();
+  }
+  sdiff = warp_sum_d(sdiff); sabs = warp_sum_d(sabs); nnan = warp_sum_d(nnan); dmax = warp_max_d(dmax);
+  if (tx == 0) { s_red[0][ty] = sdiff; s_red[1][ty] = sabs; s_red[2][ty] = dmax; s_red[3][ty] = nnan; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = -DBL_MAX, d = 0;
+    for (int w = 0; w < 8; ++w) { a += s_red[0][w]; b += s_red[1][w]; c = fmax(c, s_red[2][w]); d += s_red[3][w]; }
+    part[blockIdx.x * 4 + 0] = a; part[blockIdx.x * 4 + 1] = b; part[blockIdx.x * 4 + 2] = c; part[blockIdx.x * 4 + 3] = d;
+    __threadfence();
+    const int tk = atomicAdd(ticket, 1);
+    s_is_last = (tk == (int)gridDim.x - 1);
+    if (s_is_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (s_is_last && threadIdx.x == 0) {
+    __threadfence();
+    double a = 0, b = 0, c = -DBL_MAX, d = 0;
+    for (unsigned k = 0; k < gridDim.x; ++k) {
+      a += __ldcg(part + k * 4); b += __ldcg(part + k * 4 + 1); c = fmax(c, __ldcg(part + k * 4 + 2)); d += __ldcg(part + k * 4 + 3);
+    }
+    out4[0] = a; out4[1] = b; out4[2] = c; out4[3] = d;
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(256) k_row_sums(const double* A, int64_t nloc, int64_t ld, double* sums) {
+  __shared__ double s_red[E][8];
+  const double* row = A + static_cast<int64_t>(blockIdx.x) * ld;
+  double s[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) s[e] = 0.0;
+  for (int64_t i = threadIdx.x; i < nloc; i += 256) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) s[e] += row[i * E + e];
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    s[e] = warp_sum_d(s[e]);
+    if ((threadIdx.x & 31) == 0) s_red[e][threadIdx.x >> 5] = s[e];
+  }
+  __syncthreads();
+  if (threadIdx.x < E) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+    sums[static_cast<int64_t>(blockIdx.x) * E + threadIdx.x] = t;
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(256) k_center_sqnorm(double* A, int64_t nloc, int64_t ld, const double* sums,
+                                                       double inv_n, double* sq) {
+  __shared__ double s_red[8];
+  double* row = A + static_cast<int64_t>(blockIdx.x) * ld;
+  double mu[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) mu[e] = sums[static_cast<int64_t>(blockIdx.x) * E + e] * inv_n;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < nloc; i += 256) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const double v = row[i * E + e] - mu[e];
+      row[i * E + e] = v;
+      s += v * v;
+    }
+  }
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    sq[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_vec_max(const double* v, int64_t n, double* out2) {
+  __shared__ double s_m[8], s_n[8];
+  double mx = -DBL_MAX, nn = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) {
+    const double x = v[i];
+    if (isnan(x)) nn += 1.0; else mx = fmax(mx, x);
+  }
+  mx = warp_max_d(mx); nn = warp_sum_d(nn);
+  if ((threadIdx.x & 31) == 0) { s_m[threadIdx.x >> 5] = mx; s_n[threadIdx.x >> 5] = nn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { mx = fmax(mx, s_m[w]); nn += s_n[w]; }
+    out2[0] = mx; out2[1] = nn;
+  }
+}
+}  // namespace
+
+int launch_scan_cov(const double* A, int64_t rows, int64_t m, int64_t ld, int64_t lo, int cplx, int full_check,
+                    double* part, int* ticket, double* out4, cudaStream_t st) {
+  if (cplx) k_scan_cov<2><<<kScanBlocks, 256, 0, st>>>(A, rows, m, ld, lo, full_check, part, ticket, out4);
+  else k_scan_cov<1><<<kScanBlocks, 256, 0, st>>>(A, rows, m, ld, lo, full_check, part, ticket, out4);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_row_sums(const double* A, int64_t rows, int64_t nloc, int64_t ld, int cplx, double* sums, cudaStream_t st) {
+  if (cplx) k_row_sums<2><<<(unsigned)rows, 256, 0, st>>>(A, nloc, ld, sums);
+  else k_row_sums<1><<<(unsigned)rows, 256, 0, st>>>(A, nloc, ld, sums);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_center_sqnorm(double* A, int64_t rows, int64_t nloc, int64_t ld, int cplx, const double* sums, double inv_n,
+                         double* sq, cudaStream_t st) {
+  if (cplx) k_center_sqnorm<2><<<(unsigned)rows, 256, 0, st>>>(A, nloc, ld, sums, inv_n, sq);
+  else k_center_sqnorm<1><<<(unsigned)rows, 256, 0, st>>>(A, nloc, ld, sums, inv_n, sq);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_vec_max(const double* v, int64_t n, double* out2, cudaStream_t st) {
+  k_vec_max<<<1, 256, 0, st>>>(v, n, out2);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+
+}  // namespace speigen

@@ -1,0 +1,23 @@
+// One-time streaming passes over the resident matrix: validation (R/spEigen.R:53,75), centring (:59-60)
+// and the rho scale inputs (:72,:82).
+#pragma once
+#include "common.cuh"
+
+namespace speigen {
+
+constexpr int kScanBlocks = 148 * 4;
+
+// Covariance shard scan.  A: rows x (m * (1+cplx)) doubles, pitch ld; local row jl is global column lo+jl of S.
+// full_check != 0 (only valid when the shard is the whole matrix): out[0] = sum|S - S^H|, out[1] = sum|S|.
+// Always: out[2] = max Re diag, out[3] = number of NaN entries seen (as double).
+int launch_scan_cov(const double* A, int64_t rows, int64_t m, int64_t ld, int64_t lo, int cplx, int full_check,
+                    double* part, int* ticket, double* out4, cudaStream_t st);
+// Data shard (rows = variables, contiguous = local samples).  sums[j*(1+cplx)+e] = sum_i A[j][i]
+int launch_row_sums(const double* A, int64_t rows, int64_t nloc, int64_t ld, int cplx, double* sums, cudaStream_t st);
+// A[j][i] -= mean[j] ; sq[j] = sum_i |A[j][i]|^2   (mean = sums / n_total)
+int launch_center_sqnorm(double* A, int64_t rows, int64_t nloc, int64_t ld, int cplx, const double* sums,
+                         double inv_n, double* sq, cudaStream_t st);
+// out[0] = max_j v[j], out[1] = count of NaN in v
+int launch_vec_max(const double* v, int64_t n, double* out2, cudaStream_t st);
+
+}  // namespace speigen

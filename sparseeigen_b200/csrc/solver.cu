@@ -1,0 +1,794 @@
+// Host driver (see solver.cuh).  Reference semantics: R/spEigen.R:46-163.
+#include "solver.cuh"
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+
+namespace speigen {
+
+// ---- error / counters ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+const char* last_error() { return g_err.c_str(); }
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(); }
+
+#define SPE_TRY(x)                      \
+  do {                                  \
+    int rc__ = (x);                     \
+    if (rc__ != SPEIGEN_OK) return rc__; \
+  } while (0)
+#define SPE_NCCL(x)                                                                         \
+  do {                                                                                      \
+    int r__ = (x);                                                                          \
+    if (r__ != NCCL_SUCCESS) {                                                              \
+      set_error("NCCL error %d (%s) at %s:%d", r__, nccl_api()->GetErrorString(r__), __FILE__, __LINE__); \
+      return SPEIGEN_ERR_NCCL;                                                              \
+    }                                                                                       \
+  } while (0)
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+StageConsts make_stage(double p, double eps) {
+  StageConsts s;
+  s.p = p;
+  s.eps = eps;
+  s.c1 = std::log(1.0 + 1.0 / p);          // R/spEigen.R:110
+  s.c2 = 2.0 * (p + eps) * s.c1;           // :111
+  s.w0 = 1.0 / (eps * s.c2);               // :112
+  s.half_over_c1 = 0.5 / s.c1;             // :173
+  return s;
+}
+
+static int64_t round_up64(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// ---- creation -------------------------------------------------------------------------------------
+int Solver::create(const speigen_problem* p, const speigen_cfg* c) {
+  prob = *p;
+  cfg = *c;
+  cplx = p->is_complex ? 1 : 0;
+  data = p->is_data ? 1 : 0;
+  m = p->m;
+  n = data ? p->n : p->m;
+  q = p->q;
+  if (m < 2) { set_error("Data is univariate!"); return SPEIGEN_ERR_UNIVARIATE; }
+  if (q < 1) { set_error("The input argument q should be a positive integer."); return SPEIGEN_ERR_Q; }
+  if (q > m) { set_error("The number of estimated eigenvectors q should not be larger than rank(X)."); return SPEIGEN_ERR_RANK; }
+  if (p->world < 1 || p->local_gpus < 1 || p->rank < 0 || p->rank + p->local_gpus > p->world) {
+    set_error("bad shard description (world=%d rank=%d local=%d)", p->world, p->rank, p->local_gpus);
+    return SPEIGEN_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    set_error("no CUDA device available: speigen_b200 has no CPU fallback");
+    return SPEIGEN_ERR_NO_DEVICE;
+  }
+  if (cfg.first_device + p->local_gpus > ndev) {
+    set_error("requested %d GPUs starting at %d but only %d visible", p->local_gpus, cfg.first_device, ndev);
+    return SPEIGEN_ERR_NO_DEVICE;
+  }
+  // initialiser block: fill the DMMA n-tile (free oversampling), bounded by the attainable rank
+  const int e = 1 + cplx;
+  int b = cfg.init_block > 0 ? cfg.init_block : (cplx ? (q + 3) / 4 * 4 : (q + 7) / 8 * 8);
+  int64_t rank_cap = m;
+  if (data) rank_cap = std::min<int64_t>(m, std::max<int64_t>(n - 1, 1));
+  if (b > rank_cap) b = static_cast<int>(rank_cap);
+  if (b < q) b = q;
+  bq = b;
+  if (bq * e > kMaxCols) {
+    set_error("q = %d (%s) exceeds this build's limit of %d real columns per contraction", q, cplx ? "complex" : "real", kMaxCols);
+    return SPEIGEN_ERR_UNSUPPORTED;
+  }
+  pdq = make_dims(m, q, cplx);
+  pdb = make_dims(m, bq, cplx);
+  const int64_t shard_dim = data ? n : m;
+  rows_per_shard = (shard_dim + prob.world - 1) / prob.world;
+  mrows = padded_rows(m);
+  if (!data) mrows = std::max<int64_t>(mrows, padded_rows(rows_per_shard * prob.world));
+  devs.resize(p->local_gpus);
+  for (int i = 0; i < p->local_gpus; ++i) {
+    Dev& d = devs[i];
+    d.ordinal = cfg.first_device + i;
+    d.shard = prob.rank + i;
+    d.lo = std::min<int64_t>(shard_dim, rows_per_shard * d.shard);
+    d.hi = std::min<int64_t>(shard_dim, d.lo + rows_per_shard);
+    SPE_TRY(alloc_dev(d));
+  }
+  SPE_CUDA(cudaSetDevice(devs[0].ordinal));
+  SPE_CUDA(cudaMallocHost(&h_scal, 512 * sizeof(double)));
+  return SPEIGEN_OK;
+}
+
+int Solver::alloc_dev(Dev& d) {
+  SPE_CUDA(cudaSetDevice(d.ordinal));
+  cudaDeviceProp pr;
+  SPE_CUDA(cudaGetDeviceProperties(&pr, d.ordinal));
+  if (pr.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", d.ordinal, pr.major, pr.minor);
+    return SPEIGEN_ERR_NO_DEVICE;
+  }
+  d.num_sms = pr.multiProcessorCount;
+  SPE_CUDA(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
+  const int e = 1 + cplx;
+  if (data) { d.a_rows = m; d.a_kd = (d.hi - d.lo) * e; }
+  else { d.a_rows = d.hi - d.lo; d.a_kd = m * e; }
+  d.a_ld = round_up64(std::max<int64_t>(d.a_kd, 1), 16);
+  const size_t a_bytes = static_cast<size_t>(std::max<int64_t>(d.a_rows, 1)) * d.a_ld * sizeof(double);
+  if (cudaMalloc(&d.A, a_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("out of device memory allocating the %.2f GB matrix shard", a_bytes / 1e9);
+    return SPEIGEN_ERR_NOMEM;
+  }
+  const size_t pbytes = static_cast<size_t>(mrows) * pdb.pitch * sizeof(double);
+  for (int b = 0; b < NBUF; ++b) {
+    SPE_CUDA(cudaMalloc(&d.buf[b], pbytes));
+    SPE_CUDA(cudaMemsetAsync(d.buf[b], 0, pbytes, d.st));
+  }
+  if (cplx && !data) {
+    SPE_CUDA(cudaMalloc(&d.hat, 2 * pbytes));
+    SPE_CUDA(cudaMemsetAsync(d.hat, 0, 2 * pbytes, d.st));
+  }
+  if (data) {
+    const size_t tb = static_cast<size_t>(padded_rows(std::max<int64_t>(d.a_kd, 1))) * pdb.pitch * sizeof(double);
+    SPE_CUDA(cudaMalloc(&d.Tdata, tb));
+    SPE_CUDA(cudaMemsetAsync(d.Tdata, 0, tb, d.st));
+    if (prob.world > 1) {
+      SPE_CUDA(cudaMalloc(&d.gather, pbytes * prob.world));
+      SPE_CUDA(cudaMemsetAsync(d.gather, 0, pbytes * prob.world, d.st));
+    }
+  }
+  // contraction workspace (both forms share it; sized for the larger)
+  const int ncr_max = bq * e;
+  size_t slots = contract_workspace_slots(d.a_rows, d.num_sms);
+  size_t slot_d = contract_slot_doubles(ncr_max);
+  int ncount = static_cast<int>((d.a_rows + kTJ - 1) / kTJ);
+  if (data) {
+    slots = std::max(slots, contract_tr_workspace_slots(d.a_kd, d.num_sms));
+    ncount = std::max(ncount, static_cast<int>((d.a_kd + 127) / 128));
+  }
+  d.ws.partial_slots = slots;
+  d.ws.n_counters = ncount + 1;
+  SPE_CUDA(cudaMalloc(&d.ws.partials, slots * slot_d * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.ws.counters, d.ws.n_counters * sizeof(int)));
+  SPE_CUDA(cudaMemsetAsync(d.ws.counters, 0, d.ws.n_counters * sizeof(int), d.st));
+  const size_t glen = static_cast<size_t>(bq) * bq * e;
+  SPE_CUDA(cudaMalloc(&d.ps.gram_part, kPanelBlocks * glen * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.gram_part2, kPanelBlocks * glen * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.ps.col_part, kPanelBlocks * 2 * kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.ps.ticket, sizeof(int)));
+  SPE_CUDA(cudaMemsetAsync(d.ps.ticket, 0, sizeof(int), d.st));
+  SPE_CUDA(cudaMalloc(&d.absmin_a, kPanelBlocks * kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.absmin_b, kPanelBlocks * kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.Msmall, glen * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.evals, kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.status, sizeof(int)));
+  SPE_CUDA(cudaMemsetAsync(d.status, 0, sizeof(int), d.st));
+  SPE_CUDA(cudaMalloc(&d.dvec, kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.rho, kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.wmax, kMaxCols * sizeof(double)));
+  const size_t ntiles = static_cast<size_t>((d.a_rows + kTJ - 1) / kTJ) + 1;
+  SPE_CUDA(cudaMalloc(&d.dots_part, std::max<size_t>(ntiles, kPanelBlocks) * kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.dots_gather, static_cast<size_t>(prob.world) * kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.scal, 512 * sizeof(double)));
+  SPE_CUDA(cudaMemsetAsync(d.scal, 0, 512 * sizeof(double), d.st));
+  SPE_CUDA(cudaMalloc(&d.vecm, static_cast<size_t>(2 * m + 16) * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.vecm2, static_cast<size_t>(2 * m + 16) * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.scan_part, kScanBlocks * 4 * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.out_cm, static_cast<size_t>(m) * bq * e * sizeof(double)));
+  SPE_CUDA(cudaStreamSynchronize(d.st));
+  return SPEIGEN_OK;
+}
+
+void Solver::destroy() {
+  for (Dev& d : devs) {
+    cudaSetDevice(d.ordinal);
+    if (d.st) cudaStreamSynchronize(d.st);
+    if (d.comm && nccl_api()) nccl_api()->CommDestroy(d.comm);
+    void* ptrs[] = {d.A, d.hat, d.Tdata, d.gather, d.ws.partials, d.ws.counters, d.ps.gram_part, d.gram_part2,
+                    d.ps.col_part, d.ps.ticket, d.absmin_a, d.absmin_b, d.Msmall, d.evals, d.status, d.dvec, d.rho,
+                    d.wmax, d.dots_part, d.dots_gather, d.scal, d.vecm, d.vecm2, d.scan_part, d.out_cm, d.flush};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+    for (int b = 0; b < NBUF; ++b)
+      if (d.buf[b]) cudaFree(d.buf[b]);
+    if (d.st) cudaStreamDestroy(d.st);
+  }
+  devs.clear();
+  if (h_scal) cudaFreeHost(h_scal);
+  h_scal = nullptr;
+}
+
+int Solver::init_comm_all() {
+  if (prob.world == 1) { comm_ready = true; return SPEIGEN_OK; }
+  if (static_cast<int>(devs.size()) != prob.world) {
+    set_error("single-process communicator needs all %d shards local (have %zu)", prob.world, devs.size());
+    return SPEIGEN_ERR_ARG;
+  }
+  const NcclApi* nc = nccl_api();
+  if (!nc) return SPEIGEN_ERR_NCCL;
+  std::vector<int> ords;
+  for (Dev& d : devs) ords.push_back(d.ordinal);
+  std::vector<ncclComm_t> comms(devs.size());
+  SPE_NCCL(nc->CommInitAll(comms.data(), static_cast<int>(devs.size()), ords.data()));
+  for (size_t i = 0; i < devs.size(); ++i) devs[i].comm = comms[i];
+  comm_ready = true;
+  return SPEIGEN_OK;
+}
+
+int Solver::init_comm_rank(const void* id128) {
+  if (prob.world == 1) { comm_ready = true; return SPEIGEN_OK; }
+  const NcclApi* nc = nccl_api();
+  if (!nc) return SPEIGEN_ERR_NCCL;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  SPE_NCCL(nc->GroupStart());
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_NCCL(nc->CommInitRank(&d.comm, prob.world, id, d.shard));
+  }
+  SPE_NCCL(nc->GroupEnd());
+  comm_ready = true;
+  return SPEIGEN_OK;
+}
+
+int Solver::sync_all() {
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_CUDA(cudaStreamSynchronize(d.st));
+  }
+  return SPEIGEN_OK;
+}
+
+int Solver::read_scalars(int nd) {
+  Dev& d = devs[0];
+  SPE_CUDA(cudaSetDevice(d.ordinal));
+  SPE_CUDA(cudaMemcpyAsync(h_scal, d.scal, nd * sizeof(double), cudaMemcpyDeviceToHost, d.st));
+  SPE_CUDA(cudaStreamSynchronize(d.st));
+  return SPEIGEN_OK;
+}
+
+// ---- matrix upload / tensor maps ---------------------------------------------------------------
+int Solver::load_host(const double* X) {
+  const int e = 1 + cplx;
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    if (d.hi <= d.lo) continue;
+    if (data) {
+      // X is n x m column-major: row j of A = samples lo..hi of variable j
+      SPE_CUDA(cudaMemcpy2DAsync(d.A, d.a_ld * sizeof(double), X + d.lo * e, static_cast<size_t>(n) * e * sizeof(double),
+                                 static_cast<size_t>(d.hi - d.lo) * e * sizeof(double), static_cast<size_t>(m),
+                                 cudaMemcpyHostToDevice, d.st));
+    } else {
+      // S is m x m column-major and Hermitian: row j of A = column lo+j of S
+      SPE_CUDA(cudaMemcpy2DAsync(d.A, d.a_ld * sizeof(double), X + d.lo * m * e, static_cast<size_t>(m) * e * sizeof(double),
+                                 static_cast<size_t>(m) * e * sizeof(double), static_cast<size_t>(d.hi - d.lo),
+                                 cudaMemcpyHostToDevice, d.st));
+    }
+  }
+  SPE_TRY(sync_all());
+  loaded = true;
+  return SPEIGEN_OK;
+}
+
+int Solver::build_tensor_maps() {
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_TRY(make_stream_mat(&d.Astd, d.A, d.a_rows, d.a_kd, d.a_ld, kTJ));
+    if (data) {
+      SPE_TRY(make_stream_mat(&d.Atr, d.A, d.a_rows, d.a_kd, d.a_ld, 64));
+      d.has_tr = true;
+    }
+  }
+  return SPEIGEN_OK;
+}
+
+// ---- validation scan, centring, rho scale -------------------------------------------------------
+int Solver::prepare() {
+  const NcclApi* nc = prob.world > 1 ? nccl_api() : nullptr;
+  if (prob.world > 1 && (!nc || !comm_ready)) {
+    set_error("multi-GPU solver used before the communicator was initialised");
+    return SPEIGEN_ERR_NCCL;
+  }
+  SPE_TRY(build_tensor_maps());
+  if (!data) {
+    const int full = (prob.world == 1 && (cfg.check_symmetric || cfg.check_na)) ? 1 : 0;
+    for (Dev& d : devs) {
+      SPE_CUDA(cudaSetDevice(d.ordinal));
+      SPE_TRY(launch_scan_cov(d.A, d.a_rows, m, d.a_ld, d.lo, cplx, full, d.scan_part, d.ps.ticket, d.scal, d.st));
+    }
+    if (prob.world > 1) {
+      SPE_NCCL(nc->GroupStart());
+      for (Dev& d : devs) {
+        SPE_NCCL(nc->AllReduce(d.scal + 2, d.scal + 2, 1, NCCL_DOUBLE, NCCL_MAX, d.comm, d.st));
+        SPE_NCCL(nc->AllReduce(d.scal + 3, d.scal + 3, 1, NCCL_DOUBLE, NCCL_SUM, d.comm, d.st));
+      }
+      SPE_NCCL(nc->GroupEnd());
+    }
+    SPE_TRY(read_scalars(4));
+    if (cfg.check_na && (h_scal[3] > 0.0 || std::isnan(h_scal[1]))) {
+      set_error("This function cannot handle NAs.");
+      return SPEIGEN_ERR_NA;
+    }
+    if (full && cfg.check_symmetric) {
+      // isSymmetric.matrix: all.equal(X, Conj(t(X)), tolerance = 100 * .Machine$double.eps)   R/spEigen.R:75
+      const double tol = 100.0 * 2.220446049250313e-16;
+      const double diff = h_scal[0], sabs = h_scal[1];
+      const bool sym = (sabs > 0.0) ? (diff / sabs <= tol) : (diff == 0.0);
+      if (!sym) {
+        set_error("The covariance matrix is not symmetric.");
+        return SPEIGEN_ERR_NOT_SYMMETRIC;
+      }
+    }
+    scale_max = h_scal[2];   // max(Re(diag(X)))   R/spEigen.R:82
+  } else {
+    const int e = 1 + cplx;
+    for (Dev& d : devs) {
+      SPE_CUDA(cudaSetDevice(d.ordinal));
+      SPE_TRY(launch_row_sums(d.A, d.a_rows, d.hi - d.lo, d.a_ld, cplx, d.vecm, d.st));
+    }
+    if (prob.world > 1) {
+      SPE_NCCL(nc->GroupStart());
+      for (Dev& d : devs) SPE_NCCL(nc->AllReduce(d.vecm, d.vecm, static_cast<size_t>(m) * e, NCCL_DOUBLE, NCCL_SUM, d.comm, d.st));
+      SPE_NCCL(nc->GroupEnd());
+    }
+    for (Dev& d : devs) {
+      SPE_CUDA(cudaSetDevice(d.ordinal));
+      // scale(X, center = TRUE, scale = FALSE)   R/spEigen.R:60
+      SPE_TRY(launch_center_sqnorm(d.A, d.a_rows, d.hi - d.lo, d.a_ld, cplx, d.vecm, 1.0 / static_cast<double>(n), d.vecm2, d.st));
+    }
+    if (prob.world > 1) {
+      SPE_NCCL(nc->GroupStart());
+      for (Dev& d : devs) SPE_NCCL(nc->AllReduce(d.vecm2, d.vecm2, static_cast<size_t>(m), NCCL_DOUBLE, NCCL_SUM, d.comm, d.st));
+      SPE_NCCL(nc->GroupEnd());
+    }
+    for (Dev& d : devs) {
+      SPE_CUDA(cudaSetDevice(d.ordinal));
+      SPE_TRY(launch_vec_max(d.vecm2, m, d.scal, d.st));
+    }
+    SPE_TRY(read_scalars(2));
+    if (cfg.check_na && (h_scal[1] > 0.0 || std::isnan(h_scal[0]))) {
+      set_error("This function cannot handle NAs.");
+      return SPEIGEN_ERR_NA;
+    }
+    scale_max = h_scal[0];   // max(colSums(abs(X)^2))   R/spEigen.R:72
+  }
+  SPE_TRY(sync_all());
+  prepared = true;
+  return SPEIGEN_OK;
+}
+
+// ---- panel transfer -----------------------------------------------------------------------------
+int Solver::op_upload_panel(const double* host_cm, Buf b, const PanelDims& pd) {
+  const size_t bytes = static_cast<size_t>(pd.m) * pd.ncr * sizeof(double);
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_CUDA(cudaMemcpyAsync(d.out_cm, host_cm, bytes, cudaMemcpyHostToDevice, d.st));
+    SPE_CUDA(cudaMemsetAsync(d.buf[b], 0, static_cast<size_t>(mrows) * pd.pitch * sizeof(double), d.st));
+    SPE_TRY(launch_colmajor_to_panel(pd, d.out_cm, d.buf[b], d.st));
+  }
+  return sync_all();
+}
+
+int Solver::op_download_panel(Buf b, const PanelDims& pd, double* host_cm) {
+  Dev& d = devs[0];
+  SPE_CUDA(cudaSetDevice(d.ordinal));
+  SPE_TRY(launch_panel_to_colmajor(pd, d.buf[b], d.out_cm, d.st));
+  SPE_CUDA(cudaMemcpyAsync(host_cm, d.out_cm, static_cast<size_t>(pd.m) * pd.ncr * sizeof(double), cudaMemcpyDeviceToHost, d.st));
+  SPE_CUDA(cudaStreamSynchronize(d.st));
+  return SPEIGEN_OK;
+}
+
+int Solver::set_qvecs(const double* dv, const double* rv) {
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_CUDA(cudaMemcpyAsync(d.dvec, dv, q * sizeof(double), cudaMemcpyHostToDevice, d.st));
+    SPE_CUDA(cudaMemcpyAsync(d.rho, rv, q * sizeof(double), cudaMemcpyHostToDevice, d.st));
+  }
+  return sync_all();
+}
+
+// ---- exchange step -------------------------------------------------------------------------------
+int Solver::exchange_allgather(Buf b, const PanelDims& pd) {
+  const NcclApi* nc = nccl_api();
+  if (!nc) return SPEIGEN_ERR_NCCL;
+  const size_t count = static_cast<size_t>(rows_per_shard) * pd.pitch;
+  SPE_NCCL(nc->GroupStart());
+  for (Dev& d : devs) SPE_NCCL(nc->AllGather(d.buf[b] + d.shard * count, d.buf[b], count, NCCL_DOUBLE, d.comm, d.st));
+  SPE_NCCL(nc->GroupEnd());
+  return SPEIGEN_OK;
+}
+
+// ---- the contraction (K1 + exchange) -----------------------------------------------------------
+// outY (raw S*V or X^H X V), outB (fused reweighting), dots -> d.dots_part / n_dot_parts
+int Solver::op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vepi, bool want_dots, const StageConsts& sc) {
+  const bool multi = prob.world > 1;
+  const bool want_y = outY != NBUF, want_b = outB != NBUF;
+  const NcclApi* nc = multi ? nccl_api() : nullptr;
+  if (multi && !nc) return SPEIGEN_ERR_NCCL;
+  const bool post_unfused = data && multi;   // partial sums need the exchange before any epilogue math
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    const double* operand = d.buf[in];
+    if (!data && cplx) {
+      SPE_TRY(launch_hat(pd, d.buf[in], d.hat, /*conj_form=*/1, d.st));
+      operand = d.hat;
+    }
+    if (data) {
+      // T = X * V (local samples), then the standard form contracts over those samples
+      SPE_TRY(launch_contract_tr(d.Atr, d.buf[in], pd.ncr, d.Tdata, pd.pitch, d.ws, d.num_sms, d.st));
+      if (cplx) SPE_TRY(launch_tr_combine(d.hi - d.lo, pd.q, d.Tdata, d.Tdata, d.st));
+      operand = d.Tdata;
+    }
+    EpiArgs ep;
+    ep.q = pd.q;
+    ep.cplx = cplx;
+    ep.pitch = pd.pitch;
+    ep.sc = sc;
+    ep.row_off = data ? 0 : d.lo;
+    if (post_unfused) {
+      ep.Y = d.gather + static_cast<size_t>(d.shard) * mrows * pd.pitch;
+    } else {
+      ep.Y = want_y ? d.buf[outY] : nullptr;
+      if (want_b) { ep.B = d.buf[outB]; ep.d = d.dvec; ep.rho = d.rho; ep.wmax = d.wmax; }
+      if (want_b || want_dots) ep.V = d.buf[vepi];
+      if (want_dots) ep.dots = d.dots_part;
+    }
+    SPE_TRY(launch_contract_std(d.Astd, operand, pd.ncr, ep, d.ws, d.num_sms, d.st));
+  }
+  contractions++;
+  const int nout = pd.q;
+  if (!multi) {
+    n_dot_parts = static_cast<int>((devs[0].a_rows + kTJ - 1) / kTJ);
+    return SPEIGEN_OK;
+  }
+  if (!data) {
+    // row-sharded covariance: allgather the finished row blocks (and the per-shard dot sums)
+    if (want_y) SPE_TRY(exchange_allgather(outY, pd));
+    if (want_b) SPE_TRY(exchange_allgather(outB, pd));
+    if (want_dots) {
+      for (Dev& d : devs) {
+        SPE_CUDA(cudaSetDevice(d.ordinal));
+        const int nt = static_cast<int>((d.a_rows + kTJ - 1) / kTJ);
+        SPE_TRY(launch_sum_parts(d.dots_part, nt, nout, d.dots_gather + d.shard * nout, d.st));
+      }
+      SPE_NCCL(nc->GroupStart());
+      for (Dev& d : devs)
+        SPE_NCCL(nc->AllGather(d.dots_gather + d.shard * nout, d.dots_gather, nout, NCCL_DOUBLE, d.comm, d.st));
+      SPE_NCCL(nc->GroupEnd());
+      for (Dev& d : devs) {
+        SPE_CUDA(cudaSetDevice(d.ordinal));
+        SPE_CUDA(cudaMemcpyAsync(d.dots_part, d.dots_gather, static_cast<size_t>(prob.world) * nout * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, d.st));
+      }
+      n_dot_parts = prob.world;
+    }
+    return SPEIGEN_OK;
+  }
+  // sample-sharded data matrix: allgather the partial panels, sum them in rank order (bit-stable allreduce)
+  const size_t pcount = static_cast<size_t>(mrows) * pd.pitch;
+  SPE_NCCL(nc->GroupStart());
+  for (Dev& d : devs) SPE_NCCL(nc->AllGather(d.gather + d.shard * pcount, d.gather, pcount, NCCL_DOUBLE, d.comm, d.st));
+  SPE_NCCL(nc->GroupEnd());
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    double* ysum = want_y ? d.buf[outY] : d.buf[BT2];
+    SPE_TRY(launch_sum_panels(pd, d.gather, prob.world, pcount, ysum, d.st));
+    if (want_b)
+      SPE_TRY(launch_reweight(pd, ysum, d.buf[vepi], d.dvec, d.rho, d.wmax, sc, d.buf[outB], nullptr, d.st));
+    if (want_dots) SPE_TRY(launch_coldots(pd, d.buf[vepi], ysum, d.dots_part, d.st));
+  }
+  if (want_dots) n_dot_parts = kPanelBlocks;
+  return SPEIGEN_OK;
+}
+
+// ---- polar factor (K3 + applies):  out = in (in^H in)^{-1/2}, two Gram passes ------
+int Solver::op_polar(Buf in, Buf out, const PanelDims& pd, bool have_gram, double* /*unused*/, int which_absmin) {
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    if (!have_gram) SPE_TRY(launch_gram(pd, d.buf[in], d.buf[in], d.ps.gram_part, d.st));
+    SPE_TRY(launch_small(pd, d.ps.gram_part, kPanelBlocks, SMALL_INVSQRT, d.Msmall, d.evals, d.status, d.st));
+    SPE_TRY(launch_apply(pd, d.buf[in], d.Msmall, d.buf[BT2], d.gram_part2, nullptr, d.st));
+    SPE_TRY(launch_small(pd, d.gram_part2, kPanelBlocks, SMALL_INVSQRT, d.Msmall, d.evals, d.status, d.st));
+    double* am = which_absmin == 1 ? d.absmin_a : (which_absmin == 2 ? d.absmin_b : nullptr);
+    SPE_TRY(launch_apply(pd, d.buf[BT2], d.Msmall, d.buf[out], nullptr, am, d.st));
+  }
+  return SPEIGEN_OK;
+}
+
+// ---- initialiser: block subspace iteration with Rayleigh-Ritz (replaces eigen()/svd()) ----------
+int Solver::init_vectors(const double* V0_host, speigen_out* out) {
+  if (!prepared) SPE_TRY(prepare());
+  const double t0 = now_s();
+  const StageConsts sc0 = make_stage(0.1, 0.1);
+  int passes = 0;
+  bool converged = false;
+  double resid_rel = 0.0;
+  for (int attempt = 0; attempt < 2 && !converged; ++attempt) {
+    if (attempt == 1) {   // rank-deficient block: retry with exactly q columns
+      bq = q;
+      pdb = make_dims(m, bq, cplx);
+    }
+    for (Dev& d : devs) {
+      SPE_CUDA(cudaSetDevice(d.ordinal));
+      SPE_CUDA(cudaMemsetAsync(d.status, 0, sizeof(int), d.st));
+      SPE_CUDA(cudaMemsetAsync(d.buf[BQ], 0, static_cast<size_t>(mrows) * pdb.pitch * sizeof(double), d.st));
+      SPE_TRY(launch_random_panel(pdb, cfg.init_seed, d.buf[BQ], d.st));
+    }
+    SPE_TRY(op_polar(BQ, BQ, pdb, false, nullptr, 0));
+    double prev = 1e300;
+    int stall = 0;
+    bool rank_bad = false;
+    sv2.assign(bq, 0.0);
+    for (passes = 1; passes <= cfg.init_max_passes; ++passes) {
+      SPE_TRY(op_contract(BQ, pdb, BZ, NBUF, NBUF, false, sc0));
+      for (Dev& d : devs) {
+        SPE_CUDA(cudaSetDevice(d.ordinal));
+        SPE_TRY(launch_gram(pdb, d.buf[BQ], d.buf[BZ], d.ps.gram_part, d.st));
+        SPE_TRY(launch_small(pdb, d.ps.gram_part, kPanelBlocks, SMALL_EIGVECS, d.Msmall, d.evals, d.status, d.st));
+        SPE_TRY(launch_apply(pdb, d.buf[BQ], d.Msmall, d.buf[BV1], nullptr, nullptr, d.st));   // Ritz vectors
+        SPE_TRY(launch_apply(pdb, d.buf[BZ], d.Msmall, d.buf[BV2], nullptr, nullptr, d.st));   // S * Ritz vectors
+        SPE_TRY(launch_residual_norms(pdb, d.buf[BV2], d.buf[BV1], d.evals, d.ps, d.scal + 64, d.st));
+        SPE_CUDA(cudaMemcpyAsync(d.scal, d.evals, bq * sizeof(double), cudaMemcpyDeviceToDevice, d.st));
+      }
+      SPE_TRY(read_scalars(64 + bq));
+      for (int c = 0; c < bq; ++c) sv2[c] = h_scal[c];
+      const double th0 = std::max(std::fabs(sv2[0]), 1e-300);
+      double r = 0.0;
+      for (int c = 0; c < q; ++c) r = std::max(r, h_scal[64 + c]);
+      resid_rel = r / th0;
+      if (cfg.verbose) fprintf(stderr, "[speigen] init pass %d: theta1=%.6e theta_q=%.6e resid=%.3e\n", passes, sv2[0], sv2[q - 1], resid_rel);
+      if (!(resid_rel == resid_rel)) { set_error("This function cannot handle NAs."); return SPEIGEN_ERR_NA; }
+      if (resid_rel <= cfg.init_tol) { converged = true; break; }
+      // round-off floor: residual stopped improving at a tiny level
+      if (resid_rel > 0.5 * prev) ++stall; else stall = 0;
+      if (stall >= 3 && resid_rel <= 1e-11) { converged = true; break; }
+      prev = std::min(prev, resid_rel);
+      SPE_TRY(op_polar(BV2, BQ, pdb, false, nullptr, 0));
+      {
+        Dev& d = devs[0];
+        int st = 0;
+        SPE_CUDA(cudaSetDevice(d.ordinal));
+        SPE_CUDA(cudaMemcpyAsync(&st, d.status, sizeof(int), cudaMemcpyDeviceToHost, d.st));
+        SPE_CUDA(cudaStreamSynchronize(d.st));
+        if (st) { rank_bad = true; break; }
+      }
+    }
+    if (rank_bad) {
+      if (bq > q && attempt == 0) continue;
+      set_error("The number of estimated eigenvectors q should not be larger than rank(X).");
+      return SPEIGEN_ERR_RANK;
+    }
+    break;
+  }
+  if (passes > cfg.init_max_passes) passes = cfg.init_max_passes;
+  // checks of R/spEigen.R:69,77,79 on the Ritz values that exist
+  for (int c = 0; c < bq; ++c)
+    if (!data && sv2[c] < cfg.pd_tol) { set_error("The covariance matrix is not PD."); return SPEIGEN_ERR_NOT_PD; }
+  for (int c = 0; c < bq; ++c)
+    if (sv2[c] < 0.0) sv2[c] = 0.0;                           // :78
+  const double rank_thr = data ? cfg.rank_tol * cfg.rank_tol : cfg.rank_tol;   // :69 tests d > 1e-9 on singular values
+  if (!(sv2[q - 1] > rank_thr)) {
+    set_error("The number of estimated eigenvectors q should not be larger than rank(X).");
+    return SPEIGEN_ERR_RANK;
+  }
+  // Vx[,1:q] -> BVX ; start point V
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_CUDA(cudaMemsetAsync(d.buf[BVX], 0, static_cast<size_t>(mrows) * pdb.pitch * sizeof(double), d.st));
+    SPE_TRY(launch_take_columns(pdb, d.buf[BV1], pdq, d.buf[BVX], d.st));
+  }
+  if (V0_host) {
+    SPE_TRY(op_upload_panel(V0_host, BV, pdq));
+  } else {
+    for (Dev& d : devs) {
+      SPE_CUDA(cudaSetDevice(d.ordinal));
+      SPE_CUDA(cudaMemcpyAsync(d.buf[BV], d.buf[BVX], static_cast<size_t>(mrows) * pdq.pitch * sizeof(double), cudaMemcpyDeviceToDevice, d.st));
+    }
+  }
+  SPE_TRY(sync_all());
+  inited = true;
+  if (out) {
+    out->init_passes = passes;
+    out->init_converged = converged ? 1 : 0;
+    out->init_residual = resid_rel;
+    out->seconds_init = now_s() - t0;
+  }
+  return SPEIGEN_OK;
+}
+
+// ---- the MM loop (R/spEigen.R:105-160) ----------------------------------------------------------
+int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) {
+  if (!inited) { set_error("solver_run before solver_init"); return SPEIGEN_ERR_ARG; }
+  const double t0 = now_s();
+  std::vector<double> dv(q), rv(q);
+  if (d_in) for (int c = 0; c < q; ++c) dv[c] = d_in[c];
+  else speigen_default_d(q, dv.data());
+  // rho <- rho * max(...) * (sv2[1:q]/sv2[1]) * d/d[1]      R/spEigen.R:72,82
+  for (int c = 0; c < q; ++c) rv[c] = rho * scale_max * (sv2[c] / sv2[0]) * dv[c] / dv[0];
+  SPE_TRY(set_qvecs(dv.data(), rv.data()));
+
+  const int K = cfg.n_continuation;
+  std::vector<double> pp(K + 1), ee(K + 1), tl(K + 1);
+  speigen_schedule(&cfg, pp.data(), ee.data(), tl.data());
+  const bool fused = cfg.fused_epilogue != 0;
+  const int64_t c_before = contractions;
+
+  StageConsts sc = make_stage(pp[0], ee[0]);
+  // Y = S V for the start point; min|V| partials for the weights' column max
+  SPE_TRY(op_contract(BV, pdq, BY, NBUF, NBUF, false, sc));
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_TRY(launch_absmin(pdq, d.buf[BV], d.absmin_a, d.st));
+  }
+  Buf bV = BV, bV0 = BV0, bY = BY, bY0 = BY0;
+  bool absmin_swapped = false;   // false: accepted iterate's partials live in absmin_a
+  std::vector<double> Fv;
+  int k = 0, total_bt = 0;
+  bool hit_max = false;
+  for (int st = 0; st <= K && !hit_max; ++st) {
+    sc = make_stage(pp[st], ee[st]);
+    int flg = 1;
+    while (true) {
+      ++k;
+      // ---- V1 = MMupdate(V) ----
+      for (Dev& d : devs) {
+        SPE_CUDA(cudaSetDevice(d.ordinal));
+        SPE_TRY(launch_wmax(pdq, absmin_swapped ? d.absmin_b : d.absmin_a, sc, d.wmax, d.st));
+        SPE_TRY(launch_reweight(pdq, d.buf[bY], d.buf[bV], d.dvec, d.rho, d.wmax, sc, d.buf[BB], d.ps.gram_part, d.st));
+      }
+      const int other = absmin_swapped ? 1 : 2;   // scratch min|.| partial buffer (1 = a, 2 = b)
+      SPE_TRY(op_polar(BB, BV1, pdq, true, nullptr, other));
+      // ---- V2 = MMupdate(V1): contraction with the reweighting fused into its epilogue ----
+      for (Dev& d : devs) {
+        SPE_CUDA(cudaSetDevice(d.ordinal));
+        SPE_TRY(launch_wmax(pdq, other == 1 ? d.absmin_a : d.absmin_b, sc, d.wmax, d.st));
+      }
+      if (fused) {
+        SPE_TRY(op_contract(BV1, pdq, NBUF, BB, BV1, false, sc));
+        SPE_TRY(op_polar(BB, BV2, pdq, false, nullptr, 0));
+      } else {
+        SPE_TRY(op_contract(BV1, pdq, BT1, NBUF, NBUF, false, sc));
+        for (Dev& d : devs) {
+          SPE_CUDA(cudaSetDevice(d.ordinal));
+          SPE_TRY(launch_reweight(pdq, d.buf[BT1], d.buf[BV1], d.dvec, d.rho, d.wmax, sc, d.buf[BB], d.ps.gram_part, d.st));
+        }
+        SPE_TRY(op_polar(BB, BV2, pdq, true, nullptr, 0));
+      }
+      // ---- SQUAREM step length  (R/spEigen.R:121-123) ----
+      for (Dev& d : devs) {
+        SPE_CUDA(cudaSetDevice(d.ordinal));
+        SPE_TRY(launch_squarem_norms(pdq, d.buf[bV], d.buf[BV1], d.buf[BV2], d.ps, d.scal, d.st));
+      }
+      SPE_TRY(read_scalars(2));
+      const double nR = h_scal[0], nU = h_scal[1];
+      double a = std::min(-nR / nU, -1.0);     // nU == 0 -> -Inf as in R; NaN (0/0) -> -1
+      if (a != a) a = -1.0;
+      int nbt = 0;
+      double Fk = 0.0;
+      while (true) {                            // backtracking loop, R/spEigen.R:126-146
+        for (Dev& d : devs) {
+          SPE_CUDA(cudaSetDevice(d.ordinal));
+          SPE_TRY(launch_extrapolate(pdq, d.buf[bV], d.buf[BV1], d.buf[BV2], a, d.buf[BT1], d.ps.gram_part, d.st));
+        }
+        SPE_TRY(op_polar(BT1, bV0, pdq, true, nullptr, other));
+        SPE_TRY(op_contract(bV0, pdq, bY0, NBUF, bV0, true, sc));
+        for (Dev& d : devs) {
+          SPE_CUDA(cudaSetDevice(d.ordinal));
+          SPE_TRY(launch_objective(pdq, d.buf[bV0], sc, d.dots_part, n_dot_parts, d.dvec, d.rho, d.ps, d.scal + 8, d.st));
+        }
+        SPE_TRY(read_scalars(9));
+        Fk = h_scal[8];
+        const double Fprev = Fv.empty() ? Fk : Fv[std::max(k - 1, 1) - 1];
+        const double sgn = (Fk > 0) - (Fk < 0);
+        if (flg == 0 && Fk * (1.0 + sgn * cfg.backtrack_slack) <= Fprev && nbt < cfg.max_backtracks) {
+          a = (a - 1.0) / 2.0;                  // :141
+          ++nbt;
+        } else {
+          std::swap(bV, bV0);                   // V <- V0   :143
+          std::swap(bY, bY0);
+          absmin_swapped = !absmin_swapped;
+          break;
+        }
+      }
+      total_bt += nbt;
+      Fv.push_back(Fk);
+      if (out && k <= out->trace_capacity) {
+        if (out->F) out->F[k - 1] = Fk;
+        if (out->step_a) out->step_a[k - 1] = a;
+        if (out->backtracks_per_k) out->backtracks_per_k[k - 1] = nbt;
+        if (out->stage_of_k) out->stage_of_k[k - 1] = st + 1;
+      }
+      if (cfg.verbose) fprintf(stderr, "[speigen] stage %d k %d: nR=%.3e nU=%.3e a=%.4g bt=%d F=%.15g\n", st + 1, k, nR, nU, a, nbt, Fk);
+      if (flg == 0) {                           // stopping criterion  :149-153
+        const double Fp = Fv[k - 2];
+        const double rel = std::fabs(Fk - Fp) / std::max(1.0, std::fabs(Fp));
+        if (rel <= tl[st]) break;
+        if (k >= cfg.max_iter) { hit_max = true; break; }
+      }
+      flg = 0;
+    }
+  }
+  // threshold + normalise + outputs   :158-162
+  if (out) {
+    Dev& d = devs[0];
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    const size_t bytes = static_cast<size_t>(m) * pdq.ncr * sizeof(double);
+    if (out->vectors) {
+      SPE_TRY(launch_finalize(pdq, d.buf[bV], thres, d.ps, d.scal + 128, d.out_cm, d.st));
+      SPE_CUDA(cudaMemcpyAsync(out->vectors, d.out_cm, bytes, cudaMemcpyDeviceToHost, d.st));
+      SPE_CUDA(cudaStreamSynchronize(d.st));
+    }
+    if (out->standard_vectors) SPE_TRY(op_download_panel(BVX, pdq, out->standard_vectors));
+    if (out->values)
+      for (int c = 0; c < q; ++c) out->values[c] = data ? sv2[c] / static_cast<double>(n - 1) : sv2[c];   // :162
+    out->iterations = k;
+    out->backtracks = total_bt;
+    out->contractions = static_cast<int>(contractions - c_before);
+    out->seconds_loop = now_s() - t0;
+  }
+  {
+    Dev& d = devs[0];
+    int stt = 0;
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_CUDA(cudaMemcpyAsync(&stt, d.status, sizeof(int), cudaMemcpyDeviceToHost, d.st));
+    SPE_CUDA(cudaStreamSynchronize(d.st));
+    if (stt && cfg.verbose) fprintf(stderr, "[speigen] warning: a rank-deficient Gram matrix was met in a polar step\n");
+  }
+  SPE_TRY(sync_all());
+  return SPEIGEN_OK;
+}
+
+// ---- timing helper for bench.py (CUDA events on the launching stream) ---------------------------
+int Solver::time_contract(int ncols, int reps, int flush_l2, float* ms_each) {
+  PanelDims pd = make_dims(m, ncols, cplx);
+  if (pd.ncr > kMaxCols || ncols > bq) { set_error("time_contract: ncols %d > block %d", ncols, bq); return SPEIGEN_ERR_ARG; }
+  const size_t flush_bytes = 512ull << 20;
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_CUDA(cudaMemsetAsync(d.buf[BQ], 0, static_cast<size_t>(mrows) * pdb.pitch * sizeof(double), d.st));
+    SPE_TRY(launch_random_panel(pd, 1234, d.buf[BQ], d.st));
+    if (flush_l2 && !d.flush) SPE_CUDA(cudaMalloc(&d.flush, flush_bytes));
+  }
+  SPE_TRY(sync_all());
+  const StageConsts sc0 = make_stage(0.1, 0.1);
+  Dev& d0 = devs[0];
+  SPE_CUDA(cudaSetDevice(d0.ordinal));
+  cudaEvent_t e0, e1;
+  SPE_CUDA(cudaEventCreate(&e0));
+  SPE_CUDA(cudaEventCreate(&e1));
+  for (int r = 0; r < reps; ++r) {
+    if (flush_l2)
+      for (Dev& d : devs) {
+        SPE_CUDA(cudaSetDevice(d.ordinal));
+        SPE_CUDA(cudaMemsetAsync(d.flush, r & 0xff, flush_bytes, d.st));
+      }
+    SPE_TRY(sync_all());
+    SPE_CUDA(cudaSetDevice(d0.ordinal));
+    SPE_CUDA(cudaEventRecord(e0, d0.st));
+    SPE_TRY(op_contract(BQ, pd, BZ, NBUF, NBUF, false, sc0));
+    SPE_CUDA(cudaSetDevice(d0.ordinal));
+    SPE_CUDA(cudaEventRecord(e1, d0.st));
+    SPE_TRY(sync_all());
+    SPE_CUDA(cudaEventElapsedTime(&ms_each[r], e0, e1));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return SPEIGEN_OK;
+}
+
+}  // namespace speigen

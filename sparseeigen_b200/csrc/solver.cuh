@@ -1,0 +1,106 @@
+// Host driver of the B200 spEigen path: owns the per-GPU state, runs the block-subspace initialiser and
+// the SQUAREM-accelerated MM loop of R/spEigen.R:105-160 as a sequence of kernel launches with a handful
+// of scalar read-backs per outer iteration.  One Solver drives every GPU this process owns; replicated
+// m x q work is executed redundantly per GPU (bit-identical), the streamed matrix is sharded.
+#pragma once
+#include <vector>
+#include "../../include/speigen_b200.h"
+#include "common.cuh"
+#include "contract.cuh"
+#include "panel_ops.cuh"
+#include "matrix_ops.cuh"
+#include "nccl_shim.h"
+
+namespace speigen {
+
+enum Buf { BV = 0, BV1, BV2, BV0, BY, BY0, BB, BT1, BT2, BVX, BQ, BZ, NBUF };
+
+struct Dev {
+  int ordinal = 0;
+  int shard = 0;
+  cudaStream_t st = nullptr;
+  int num_sms = 148;
+  // streamed matrix shard
+  double* A = nullptr;
+  int64_t a_rows = 0, a_kd = 0, a_ld = 0;   // rows, contiguous doubles, pitch
+  int64_t lo = 0, hi = 0;                   // owned global range (rows of S / samples of X)
+  StreamMat Astd, Atr;
+  bool has_tr = false;
+  // panels
+  double* buf[NBUF] = {};
+  double* hat = nullptr;       // complex operand expansion (2*mrows) / generic operand scratch
+  double* Tdata = nullptr;     // data mode: X*V (local samples), hat-expanded for complex
+  double* gather = nullptr;    // data mode multi-GPU: [world][panel] partials
+  ContractWorkspace ws;
+  PanelScratch ps;
+  double* gram_part2 = nullptr;
+  double* absmin_a = nullptr;  // min|.| partials of V (accepted iterate)
+  double* absmin_b = nullptr;  // min|.| partials of V1 / V0 candidates
+  double* Msmall = nullptr;
+  double* evals = nullptr;
+  int* status = nullptr;
+  double* dvec = nullptr;
+  double* rho = nullptr;
+  double* wmax = nullptr;
+  double* dots_part = nullptr;
+  double* dots_gather = nullptr;
+  double* scal = nullptr;      // device scalars [256]
+  double* vecm = nullptr;      // length-2m scratch (row sums etc.)
+  double* vecm2 = nullptr;
+  double* scan_part = nullptr;
+  double* out_cm = nullptr;    // column-major staging for D2H (m*q*(1+cplx))
+  double* flush = nullptr;     // L2 flush buffer (timing only)
+  ncclComm_t comm = nullptr;
+};
+
+class Solver {
+ public:
+  speigen_problem prob{};
+  speigen_cfg cfg{};
+  std::vector<Dev> devs;
+  int cplx = 0, data = 0;
+  int64_t m = 0, n = 0;
+  int q = 0;          // requested eigenvectors
+  int bq = 0;         // initialiser block size (>= q)
+  int64_t mrows = 0;  // allocated panel rows
+  int64_t rows_per_shard = 0;
+  PanelDims pdq, pdb;
+  double* h_scal = nullptr;   // pinned
+  bool loaded = false, prepared = false, inited = false, comm_ready = false;
+  double scale_max = 0.0;     // max Re diag S (cov) or max_j sum_i |X_ij|^2 (data)
+  std::vector<double> sv2;    // top-bq Ritz values
+  int64_t contractions = 0;
+  int n_dot_parts = 0;        // partial count of the last contraction's column dots
+
+  int create(const speigen_problem* p, const speigen_cfg* c);
+  void destroy();
+  int init_comm_all();
+  int init_comm_rank(const void* id128);
+  int load_host(const double* X);
+  int build_tensor_maps();
+  int prepare();
+  int init_vectors(const double* V0_host, speigen_out* out);
+  int run(double rho, const double* d, double thres, speigen_out* out);
+
+  // building blocks (all devices)
+  int op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vepi, bool want_dots, const StageConsts& sc);
+  int op_polar(Buf in, Buf out, const PanelDims& pd, bool have_gram, double* absmin_of_out_sel /*0,1*/, int which);
+  int op_upload_panel(const double* host_cm, Buf b, const PanelDims& pd);
+  int op_download_panel(Buf b, const PanelDims& pd, double* host_cm);
+  int sync_all();
+  int read_scalars(int ndoubles);   // device 0 scal -> h_scal
+  int set_qvecs(const double* d, const double* rho);
+  int time_contract(int ncols, int reps, int flush_l2, float* ms_each);
+  int exchange_allgather(Buf b, const PanelDims& pd);
+
+ private:
+  int alloc_dev(Dev& d);
+};
+
+StageConsts make_stage(double p, double eps);
+
+}  // namespace speigen
+
+struct speigen_solver {
+  speigen::Solver impl;
+};
