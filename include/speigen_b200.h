@@ -158,6 +158,18 @@ int speigen_solver_eig_small(speigen_solver* s, const double* C_host, int32_t n,
 /* timing: `reps` back-to-back contractions of a resident random panel, CUDA events on the launching stream,
  * L2 flushed between repetitions when flush_l2 != 0.  ms_each[reps]. */
 int speigen_solver_time_contract(speigen_solver* s, int32_t ncols, int32_t reps, int32_t flush_l2, float* ms_each);
+/* Device-to-device load of shard `local_idx` from a caller buffer already in HBM (same row meaning as
+ * speigen_solver_shard_buffer; src_ld = source row pitch in doubles). */
+int speigen_solver_load_device(speigen_solver* s, int32_t local_idx, const double* dev_src, int64_t src_ld);
+/* `nsteps` back-to-back MM updates V <- spEigenMMupdate(V) (R/spEigen.R:167-183) on the resident iterate at
+ * continuation stage `stage` (0-based).  ms_out == NULL: asynchronous.  ms_out != NULL: the nsteps are bracketed by
+ * CUDA events on the launching stream (synchronised on both sides) and the elapsed device time is returned. */
+int speigen_solver_mm_steps(speigen_solver* s, int32_t nsteps, int32_t stage, double rho, const double* d_or_null,
+                            float* ms_out);
+int speigen_solver_sync(speigen_solver* s);
+/* CUDA-event timing of the contraction kernel launches of local device 0 (for the roofline line of bench.py). */
+int speigen_solver_kernel_timing(speigen_solver* s, int32_t enable);
+int speigen_solver_kernel_time(speigen_solver* s, double* ms_total, int32_t* launches);
 int64_t speigen_solver_launch_count(speigen_solver* s);
 int speigen_solver_stream(speigen_solver* s, int32_t local_idx, void** cuda_stream);
 

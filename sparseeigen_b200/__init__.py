@@ -107,6 +107,11 @@ def lib():
     L.speigen_solver_launch_count.argtypes = [C.c_void_p]
     L.speigen_solver_launch_count.restype = C.c_int64
     L.speigen_solver_stream.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+    L.speigen_solver_load_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+    L.speigen_solver_mm_steps.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, _dp, C.POINTER(C.c_float)]
+    L.speigen_solver_sync.argtypes = [C.c_void_p]
+    L.speigen_solver_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
+    L.speigen_solver_kernel_time.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int32)]
     _lib = L
     return L
 
@@ -365,6 +370,27 @@ class Solver:
         ms = (C.c_float * reps)()
         _check(self.L.speigen_solver_time_contract(self.h, ncols, reps, 1 if flush_l2 else 0, ms))
         return np.array(ms[:], dtype=np.float64)
+
+    def load_device(self, dev_ptr: int, src_ld: int, local_idx=0):
+        _check(self.L.speigen_solver_load_device(self.h, local_idx, C.c_void_p(dev_ptr), src_ld))
+
+    def mm_steps(self, nsteps, stage=0, rho=0.5, d=None, timed=False):
+        """nsteps MM updates on the resident iterate; timed=True returns the CUDA-event elapsed ms."""
+        dd = None if d is None else np.ascontiguousarray(d, dtype=np.float64)
+        ms = C.c_float(0.0)
+        _check(self.L.speigen_solver_mm_steps(self.h, nsteps, stage, float(rho), _ptr(dd), C.byref(ms) if timed else None))
+        return ms.value if timed else None
+
+    def sync(self):
+        _check(self.L.speigen_solver_sync(self.h))
+
+    def kernel_timing(self, enable=True):
+        _check(self.L.speigen_solver_kernel_timing(self.h, 1 if enable else 0))
+
+    def kernel_time(self):
+        ms, n = C.c_double(), C.c_int32()
+        _check(self.L.speigen_solver_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def launch_count(self) -> int:
         return int(self.L.speigen_solver_launch_count(self.h))

@@ -266,6 +266,21 @@ int speigen_solver_time_contract(speigen_solver* s, int32_t ncols, int32_t reps,
   return S.time_contract(ncols, reps, flush_l2, ms_each);
 }
 
+int speigen_solver_load_device(speigen_solver* s, int32_t li, const double* dev_src, int64_t src_ld) {
+  return s->impl.load_device(li, dev_src, src_ld);
+}
+int speigen_solver_mm_steps(speigen_solver* s, int32_t nsteps, int32_t stage, double rho, const double* d, float* ms_out) {
+  return s->impl.mm_steps(nsteps, stage, rho, d, ms_out);
+}
+int speigen_solver_sync(speigen_solver* s) { return s->impl.sync_all(); }
+int speigen_solver_kernel_timing(speigen_solver* s, int32_t enable) { s->impl.enable_kernel_timing(enable != 0); return SPEIGEN_OK; }
+int speigen_solver_kernel_time(speigen_solver* s, double* ms_total, int32_t* launches) {
+  int n = 0;
+  const int rc = s->impl.kernel_time(ms_total, &n);
+  *launches = n;
+  return rc;
+}
+
 // ---- one-shot drop-in calls -------------------------------------------------------------------
 static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data, int is_complex, double q, double rho,
                        const double* d, const double* V0, double thres, const speigen_cfg* cfg_in, speigen_out* out) {

@@ -448,7 +448,10 @@ int Solver::op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vep
       if (want_b || want_dots) ep.V = d.buf[vepi];
       if (want_dots) ep.dots = d.dots_part;
     }
+    const bool tme = ktiming && (&d == &devs[0]) && kev_used + 2 <= kev.size();
+    if (tme) SPE_CUDA(cudaEventRecord(kev[kev_used], d.st));
     SPE_TRY(launch_contract_std(d.Astd, operand, pd.ncr, ep, d.ws, d.num_sms, d.st));
+    if (tme) { SPE_CUDA(cudaEventRecord(kev[kev_used + 1], d.st)); kev_used += 2; }
   }
   contractions++;
   const int nout = pd.q;
@@ -750,6 +753,85 @@ int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) 
     if (stt && cfg.verbose) fprintf(stderr, "[speigen] warning: a rank-deficient Gram matrix was met in a polar step\n");
   }
   SPE_TRY(sync_all());
+  return SPEIGEN_OK;
+}
+
+// ---- bench helpers ------------------------------------------------------------------------------
+void Solver::enable_kernel_timing(bool on) {
+  if (on && kev.empty()) {
+    cudaSetDevice(devs[0].ordinal);
+    kev.resize(8192);
+    for (auto& e : kev) cudaEventCreate(&e);
+  }
+  ktiming = on;
+  kev_used = 0;
+}
+int Solver::kernel_time(double* ms_total, int* launches) {
+  SPE_TRY(sync_all());
+  double t = 0.0;
+  for (size_t i = 0; i + 1 < kev_used; i += 2) {
+    float ms = 0.f;
+    SPE_CUDA(cudaEventElapsedTime(&ms, kev[i], kev[i + 1]));
+    t += ms;
+  }
+  *ms_total = t;
+  *launches = static_cast<int>(kev_used / 2);
+  kev_used = 0;
+  return SPEIGEN_OK;
+}
+
+int Solver::load_device(int li, const double* src, int64_t src_ld) {
+  if (li < 0 || li >= static_cast<int>(devs.size())) return SPEIGEN_ERR_ARG;
+  Dev& d = devs[li];
+  SPE_CUDA(cudaSetDevice(d.ordinal));
+  SPE_CUDA(cudaMemcpy2DAsync(d.A, d.a_ld * sizeof(double), src, src_ld * sizeof(double), d.a_kd * sizeof(double),
+                             static_cast<size_t>(d.a_rows), cudaMemcpyDeviceToDevice, d.st));
+  SPE_CUDA(cudaStreamSynchronize(d.st));
+  loaded = true;
+  return SPEIGEN_OK;
+}
+
+int Solver::mm_steps(int nsteps, int stage, double rho, const double* d_in, float* ms_out) {
+  if (!inited) { set_error("mm_steps before solver_init"); return SPEIGEN_ERR_ARG; }
+  std::vector<double> dv(q), rv(q);
+  if (d_in) for (int c = 0; c < q; ++c) dv[c] = d_in[c];
+  else speigen_default_d(q, dv.data());
+  for (int c = 0; c < q; ++c) rv[c] = rho * scale_max * (sv2[c] / sv2[0]) * dv[c] / dv[0];
+  SPE_TRY(set_qvecs(dv.data(), rv.data()));
+  const int K = cfg.n_continuation;
+  std::vector<double> pp(K + 1), ee(K + 1), tl(K + 1);
+  speigen_schedule(&cfg, pp.data(), ee.data(), tl.data());
+  if (stage < 0 || stage > K) stage = 0;
+  const StageConsts sc = make_stage(pp[stage], ee[stage]);
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_TRY(launch_absmin(pdq, d.buf[BV], d.absmin_a, d.st));
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ms_out) {
+    SPE_TRY(sync_all());
+    SPE_CUDA(cudaSetDevice(devs[0].ordinal));
+    SPE_CUDA(cudaEventCreate(&e0));
+    SPE_CUDA(cudaEventCreate(&e1));
+    SPE_CUDA(cudaEventRecord(e0, devs[0].st));
+  }
+  for (int i = 0; i < nsteps; ++i) {
+    for (Dev& d : devs) {
+      SPE_CUDA(cudaSetDevice(d.ordinal));
+      SPE_TRY(launch_wmax(pdq, d.absmin_a, sc, d.wmax, d.st));
+    }
+    SPE_TRY(op_contract(BV, pdq, NBUF, BB, BV, false, sc));     // K1 with the fused reweighting epilogue
+    SPE_TRY(op_polar(BB, BV1, pdq, false, nullptr, 1));         // K3 (+ min|V| partials for the next weights)
+    for (Dev& d : devs) std::swap(d.buf[BV], d.buf[BV1]);
+  }
+  if (ms_out) {
+    SPE_CUDA(cudaSetDevice(devs[0].ordinal));
+    SPE_CUDA(cudaEventRecord(e1, devs[0].st));
+    SPE_TRY(sync_all());
+    SPE_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
   return SPEIGEN_OK;
 }
 

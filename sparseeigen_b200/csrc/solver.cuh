@@ -70,7 +70,10 @@ class Solver {
   double scale_max = 0.0;     // max Re diag S (cov) or max_j sum_i |X_ij|^2 (data)
   std::vector<double> sv2;    // top-bq Ritz values
   int64_t contractions = 0;
-  int n_dot_parts = 0;        // partial count of the last contraction's column dots
+  int n_dot_parts = 0;
+  bool ktiming = false;
+  std::vector<cudaEvent_t> kev;   // event pairs around device 0's contraction launches
+  size_t kev_used = 0;        // partial count of the last contraction's column dots
 
   int create(const speigen_problem* p, const speigen_cfg* c);
   void destroy();
@@ -91,6 +94,12 @@ class Solver {
   int read_scalars(int ndoubles);   // device 0 scal -> h_scal
   int set_qvecs(const double* d, const double* rho);
   int time_contract(int ncols, int reps, int flush_l2, float* ms_each);
+  // bench: `nsteps` back-to-back MM updates V <- spEigenMMupdate(V) (R/spEigen.R:167-183) at continuation stage `stage`
+  int mm_steps(int nsteps, int stage, double rho, const double* d, float* ms_out);
+  int load_device(int local_idx, const double* dev_src, int64_t src_ld);
+  // per-launch device timing of the contraction kernel (CUDA events on the launching stream of device 0)
+  void enable_kernel_timing(bool on);
+  int kernel_time(double* ms_total, int* launches);
   int exchange_allgather(Buf b, const PanelDims& pd);
 
  private:

@@ -1,0 +1,294 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes), against the oracle on the
+same seeded inputs, against the golden fixtures, and through size-independent properties at full size.
+
+Tolerances (FP64 path, north_star): single kernels <= 1e-12 relative; objective trajectory <= 1e-10
+relative on the pre-round-off prefix (iterations whose SQUAREM step |a| < 1e3); end to end:
+identical support after thresholding and per-column |<u_ref, u_gpu>| >= 1 - 1e-5 (the oracle's own
+1-ulp noise floor is measured in the same test and must be of the same order)."""
+import numpy as np
+import pytest
+
+import sparseeigen_b200 as sb
+from oracle import speigen_oracle as o
+from conftest import colwise_inner
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def herm(rng, m, cplx):
+    A = rng.standard_normal((m, m)) + (1j * rng.standard_normal((m, m)) if cplx else 0)
+    return (A + np.conj(A.T)) / 2
+
+
+def panel(rng, m, q, cplx):
+    return rng.standard_normal((m, q)) + (1j * rng.standard_normal((m, q)) if cplx else 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1: contraction
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,q", [(2, 1), (17, 3), (64, 8), (255, 9), (257, 16), (500, 3), (1000, 20), (2049, 1),
+                                 (3000, 24), (1500, 33), (1024, 64)])
+def test_contract_real_cov(m, q):
+    rng = np.random.default_rng(m * 100 + q)
+    S = herm(rng, m, False)
+    with sb.Solver(m, min(q, m)) as s:
+        s.load(S)
+        U = panel(rng, m, min(q, m), False)
+        assert rel(s.contract(U), S @ U) < 1e-13
+
+
+@pytest.mark.parametrize("m,q", [(3, 1), (300, 3), (1001, 5), (777, 20), (512, 32)])
+def test_contract_complex_cov(m, q):
+    rng = np.random.default_rng(m + q)
+    S = herm(rng, m, True)
+    with sb.Solver(m, min(q, m), is_complex=True) as s:
+        s.load(S)
+        U = panel(rng, m, min(q, m), True)
+        assert rel(s.contract(U), S @ U) < 1e-13
+
+
+@pytest.mark.parametrize("n,m,q,cplx", [(15, 10, 3, False), (300, 200, 3, False), (1203, 515, 4, False), (64, 700, 8, False),
+                                        (301, 200, 3, True), (2000, 333, 20, True)])
+def test_contract_data(n, m, q, cplx):
+    rng = np.random.default_rng(n + m)
+    X = panel(rng, n, m, cplx)
+    with sb.Solver(m, q, n=n, is_complex=cplx, is_data=True) as s:
+        s.load(X)
+        U = panel(rng, m, q, cplx)
+        assert rel(s.contract(U), np.conj(X.T) @ (X @ U)) < 1e-13
+
+
+def test_contract_is_deterministic_and_linear():
+    rng = np.random.default_rng(1)
+    m, q = 4000, 20
+    S = herm(rng, m, False)
+    with sb.Solver(m, q) as s:
+        s.load(S)
+        U, W = panel(rng, m, q, False), panel(rng, m, q, False)
+        Y1, Y2 = s.contract(U), s.contract(U)
+        assert np.array_equal(Y1, Y2)                                  # fixed-order split-K fix-up
+        assert rel(s.contract(2.0 * U - 3.0 * W), 2.0 * Y1 - 3.0 * s.contract(W)) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------
+# K3: polar factor / small eigen-solver
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,q,cplx,cond", [(50, 3, False, 1e0), (1500, 10, False, 1e4), (3000, 20, False, 1e5),
+                                           (700, 7, True, 1e3), (999, 20, True, 1e4), (2000, 64, False, 1e2)])
+def test_polar(m, q, cplx, cond):
+    rng = np.random.default_rng(q)
+    A = panel(rng, m, q, cplx) * np.logspace(0, np.log10(cond), q)[None, :]
+    with sb.Solver(m, q, is_complex=cplx) as s:
+        U = s.polar(A)
+    assert np.abs(np.conj(U.T) @ U - np.eye(q)).max() < 1e-13
+    assert rel(U, o.polar(A)) < 1e-15 * cond * 50 + 1e-13
+
+
+@pytest.mark.parametrize("n,cplx", [(1, False), (2, False), (3, False), (8, False), (19, False), (24, False), (7, True), (20, True)])
+def test_eig_small_jacobi(n, cplx):
+    rng = np.random.default_rng(n)
+    B = panel(rng, 3 * n + 2, n, cplx)
+    Cm = np.conj(B.T) @ B
+    with sb.Solver(64, min(n, 64), is_complex=cplx, init_block=n) as s:
+        ev, W = s.eig_small(Cm)
+    ref = np.linalg.eigvalsh(Cm)[::-1]
+    assert np.allclose(ev, ref, rtol=1e-12, atol=1e-13 * ref.max())
+    assert np.abs(Cm @ W - W * ev[None, :]).max() < 1e-12 * ref.max()
+    assert np.abs(np.conj(W.T) @ W - np.eye(n)).max() < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------
+# single MM update / objective against the golden known answers and the oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["real_cov", "real_data", "cplx_cov", "cplx_data"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_mm_update_and_objective_golden(golden, name, fused):
+    X, q = golden[f"{name}.X"], int(golden[f"{name}.q"])
+    data = bool(golden[f"{name}.data"])
+    cplx = np.iscomplexobj(X)
+    prob = o.setup(X, q, float(golden[f"{name}.rho"]), data)
+    pp, Eps, _ = o.schedule()
+    n, m = X.shape
+    with sb.Solver(m, q, n=n if data else 0, is_complex=cplx, is_data=data) as s:
+        s.load(X)
+        if data:
+            s.prepare()                                   # centring happens on the device (R/spEigen.R:60)
+        for st in (0, 5, 10):
+            V1 = s.mm_update(prob.V, prob.d, prob.rho_vec, pp[st], Eps[st], fused=fused)
+            assert rel(V1, golden[f"{name}.mm{st}"]) < 1e-11, (name, st)
+            F = s.objective(golden[f"{name}.mm{st}"], prob.d, prob.rho_vec, pp[st], Eps[st])
+            Fg = float(golden[f"{name}.obj{st}"])
+            assert abs(F - Fg) <= 1e-12 * max(1.0, abs(Fg)), (name, st, F, Fg)
+
+
+def test_fused_and_unfused_epilogue_agree_bitwise():
+    X, _ = o.spiked_samples(900, 200, 5, 0.05, seed=4)
+    S = o.sample_cov(X)
+    prob = o.setup(S, 5, mode="direct")
+    pp, Eps, _ = o.schedule()
+    with sb.Solver(900, 5) as s:
+        s.load(S)
+        a = s.mm_update(prob.V, prob.d, prob.rho_vec, pp[3], Eps[3], fused=True)
+        b = s.mm_update(prob.V, prob.d, prob.rho_vec, pp[3], Eps[3], fused=False)
+    assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------
+# end to end against the oracle
+# ---------------------------------------------------------------------------------------------------
+def _e2e(X, q, data=False, rho=0.5, **kw):
+    r = sb.spEigen(X, q, rho=rho, data=data, **kw)
+    ro = o.spEigen(X, q, rho=rho, data=data, mode="direct", return_trace=True,
+                   **{k: v for k, v in kw.items() if k in ("d", "V", "thres")})
+    tr = ro["trace"]
+    F, Fo = r["info"]["F"], np.array(tr.F)
+    # prefix of the trajectory that is not round-off dominated (|a| < 1e3 in both runs so far)
+    n = 0
+    for k in range(min(len(F), len(Fo))):
+        if abs(tr.a_init[k]) > 1e3 or abs(r["info"]["step_a"][k]) > 1e3:
+            break
+        n = k + 1
+    assert n >= 8
+    assert np.max(np.abs(F[:n] - Fo[:n]) / np.maximum(1.0, np.abs(Fo[:n]))) < 1e-10
+    assert np.array_equal(r["info"]["stage_of_k"][:n], np.array(tr.stage)[:n])
+    assert np.array_equal(r["vectors"] != 0, ro["vectors"] != 0)                      # identical support
+    assert np.all(colwise_inner(r["vectors"], ro["vectors"]) > 1 - 1e-5)
+    assert np.allclose(r["values"], ro["values"], rtol=1e-11)
+    assert np.all(colwise_inner(r["standard_vectors"], ro["standard_vectors"]) > 1 - 1e-10)
+    G = np.conj(r["vectors"].T) @ r["vectors"]
+    assert np.abs(np.diag(G) - 1).max() < 1e-12
+    assert abs(F[-1] - Fo[-1]) / abs(Fo[-1]) < 1e-4
+    return r, ro
+
+
+def test_e2e_readme_config():
+    """configs[0]: README example spEigen(cov(X), q=3), m=500, n=100 (README.md:56-108)."""
+    X, Vq = o.spiked_samples(500, 100, 3, 0.1, seed=42)
+    r, ro = _e2e(o.sample_cov(X), 3)
+    assert np.all(colwise_inner(r["vectors"], Vq) >= 0.997)
+    assert np.array_equal((r["vectors"] != 0).sum(axis=0), [50, 50, 50])
+    # the oracle's own noise floor: same code, S perturbed by 1 ulp
+    S = o.sample_cov(X)
+    Sp = S * (1 + np.finfo(float).eps * np.sign(np.random.default_rng(0).standard_normal(S.shape)))
+    Sp = (Sp + Sp.T) / 2
+    rp = o.spEigen(Sp, 3, mode="direct")
+    floor = 1 - colwise_inner(rp["vectors"], ro["vectors"]).min()
+    ours = 1 - colwise_inner(r["vectors"], ro["vectors"]).min()
+    print(f"noise floor (oracle vs 1-ulp-perturbed oracle): {floor:.2e}; GPU vs oracle: {ours:.2e}")
+    assert ours < max(1e3 * floor, 1e-5)
+
+
+def test_e2e_data_matrix():
+    X, _ = o.spiked_samples(500, 100, 3, 0.1, seed=42)
+    _e2e(X, 3, data=True)
+
+
+def test_e2e_config2_m5000_q10():
+    """configs[1]: covariance input m=5000, q=10."""
+    X, _ = o.spiked_samples(5000, 1000, 10, 0.05, seed=42)
+    _e2e(o.sample_cov(X), 10)
+
+
+def test_e2e_complex_cov_and_data():
+    Xc, _ = o.spiked_samples(400, 500, 3, 0.2, seed=1, cplx=True)
+    _e2e(o.sample_cov(Xc), 3)
+    _e2e(Xc, 3, data=True, rho=0.6)
+
+
+def test_e2e_custom_d_V_thres_q1():
+    X, _ = o.spiked_samples(300, 120, 4, 0.1, seed=8)
+    S = o.sample_cov(X)
+    prob = o.setup(S, 4)
+    _e2e(S, 4, d=np.array([1.0, 0.9, 0.8, 0.7]))
+    _e2e(S, 4, V=prob.V[:, ::-1].copy() * np.array([1, -1, 1, -1])[None, :])
+    r = sb.spEigen(S, 1)
+    assert r["vectors"].shape == (300, 1) and abs(np.linalg.norm(r["vectors"]) - 1) < 1e-12
+    big = sb.spEigen(S, 4, thres=0.05)
+    assert np.all((np.abs(big["vectors"]) == 0) | (np.abs(big["vectors"]) >= 0.05 * 0.99))
+
+
+@pytest.mark.parametrize("name", ["real_cov", "real_data", "cplx_cov", "cplx_data"])
+def test_e2e_golden(golden, name):
+    X, q = golden[f"{name}.X"], int(golden[f"{name}.q"])
+    r = sb.spEigen(X, q, rho=float(golden[f"{name}.rho"]), data=bool(golden[f"{name}.data"]))
+    assert np.allclose(r["values"], golden[f"{name}.values"], rtol=1e-11)
+    assert np.array_equal(r["vectors"] != 0, golden[f"{name}.vectors"] != 0)
+    assert np.all(colwise_inner(r["vectors"], golden[f"{name}.vectors"]) > 1 - 1e-5)
+    F, Fg = r["info"]["F"], golden[f"{name}.F"]
+    assert np.allclose(F[:8], Fg[:8], rtol=1e-10)
+
+
+def test_run_is_bit_reproducible():
+    X, _ = o.spiked_samples(800, 200, 5, 0.05, seed=6)
+    S = o.sample_cov(X)
+    a, b = sb.spEigen(S, 5), sb.spEigen(S, 5)
+    assert np.array_equal(a["vectors"], b["vectors"]) and np.array_equal(a["info"]["F"], b["info"]["F"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's behavioural tests at the boundary (tests/testthat/test-sparseEigen.R)
+# ---------------------------------------------------------------------------------------------------
+def test_reference_testthat_behaviours():
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((15, 10))
+    S = np.cov(X, rowvar=False)
+    for args, kw in (((X, 3, 0.5), dict(data=True)), ((S, 3, 0.5), {})):               # :55-70 output lengths
+        r = sb.spEigen(*args, **kw)
+        assert r["vectors"].size == 30 and r["values"].size == 3 and r["standard_vectors"].size == 30
+    # NA found by the device scan when the host pre-check is bypassed (call the C ABI directly)   :1-18
+    import ctypes as C
+    L = sb.lib()
+    Sna = np.asfortranarray(S.copy()); Sna[2, 3] = np.nan; Sna[3, 2] = np.nan
+    ob = sb._OutBuffers(10, 3, False)
+    rc = L.speigen_run_f64(Sna.ctypes.data_as(sb._dp), 10, 10, 0, 3.0, 0.5, None, None, 1e-9, None, C.byref(ob.c))
+    assert rc == 2
+    A = S.copy(); A[0, 1] += 1e-3
+    with pytest.raises(sb.SpEigenError, match="not symmetric"): sb.spEigen(A, 3)        # R/spEigen.R:75
+    with pytest.raises(sb.SpEigenError, match="not PD"): sb.spEigen(S - 5 * np.eye(10), 3)   # :77
+    low = X[:3].T @ X[:3]
+    with pytest.raises(sb.SpEigenError, match="rank"): sb.spEigen(low, 5)               # :79
+    with pytest.raises(sb.SpEigenError, match="rank"): sb.spEigen(X[:3], 5, data=True)  # :69
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE config 4: m = 50000, q = 20) — no oracle at this size
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_properties():
+    import torch
+    from bench import synth_cov_rows, symmetrize_
+    m, n, q = 50000, 10000, 20
+    S = symmetrize_(synth_cov_rows(m, n, q, 0.02, 0, m, torch.device("cuda", 0)))
+    with sb.Solver(m, q) as s:
+        s.init_comm(None)
+        s.load_device(S.data_ptr(), m)
+        rng = np.random.default_rng(0)
+        U, W = rng.standard_normal((m, q)), rng.standard_normal((m, q))
+        YU, YW = s.contract(U), s.contract(W)
+        # linearity and symmetry of the operator: S(aU+bW) = aSU + bSW ;  W^T (S U) = (S W)^T U
+        assert rel(s.contract(0.5 * U - 2.0 * W), 0.5 * YU - 2.0 * YW) < 1e-13
+        assert np.abs(W.T @ YU - (U.T @ YW).T).max() / np.abs(W.T @ YU).max() < 1e-12
+        # spot check 64 rows against a host dot product
+        rows = rng.choice(m, 64, replace=False)
+        Srows = S[torch.as_tensor(rows, device=S.device)].cpu().numpy()
+        assert rel(YU[rows], Srows @ U) < 1e-13
+        del S
+        torch.cuda.empty_cache()
+        s.prepare()
+        info = s.init()
+        assert info["init_converged"] and info["init_residual"] < 1e-12
+        r = s.run(rho=0.5)
+    V = r["vectors"]
+    assert np.abs(V.T @ V - np.eye(q)).max() < 1e-6           # thresholded + renormalised orthonormal iterate
+    assert np.array_equal((V != 0).sum(axis=0), np.full(q, 1000))     # planted cardinality 0.02 m
+    for j in range(q):
+        assert np.all(V[j * 1000:(j + 1) * 1000, j] != 0)
+    F, st = r["info"]["F"], r["info"]["stage_of_k"]
+    for k in range(1, len(F)):
+        if st[k] == st[k - 1]:
+            assert F[k] * (1 + np.sign(F[k]) * 1e-9) > F[k - 1]  # accepted steps are monotone within a stage
+    assert np.all(np.diff(r["values"]) < 0)

@@ -1,0 +1,106 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/*.h declares,
+and its host-only logic (validation, schedule, defaults, sharding) agrees with the oracle.  No compute
+calls are made without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sparseeigen_b200 as sb
+from oracle import speigen_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "speigen_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(speigen_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = sb.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/speigen_b200.h but not exported"
+    assert L.speigen_abi_version() == 1
+
+
+def test_validate_args_matches_reference_conditions():
+    L = sb.lib()
+    assert L.speigen_validate_args(15, 10, 3.0, 0.5) == 0
+    assert L.speigen_validate_args(15, 1, 3.0, 0.5) == 1          # univariate      R/spEigen.R:52
+    assert L.speigen_validate_args(15, 10, float("nan"), 0.5) == 2   # NA           :53
+    assert L.speigen_validate_args(15, 10, 3.0, float("nan")) == 2
+    for q in (-1.0, 0.0, 0.5):
+        assert L.speigen_validate_args(15, 10, q, 0.5) == 3       # q               :54
+    assert L.speigen_validate_args(15, 10, 3.0, 0.0) == 4         # rho <= 0        :55
+    assert b"positive" in L.speigen_last_error()
+
+
+def test_schedule_defaults_stage_constants_match_oracle():
+    p, e, t = sb.schedule()
+    po, eo, to = o.schedule()
+    assert np.allclose(p, po, rtol=1e-15) and np.allclose(e, eo, rtol=1e-15) and np.allclose(t, to, rtol=1e-15)
+    for q in (1, 2, 3, 20):
+        assert np.allclose(sb.default_d(q), o.default_d(q), rtol=1e-15)
+    L = sb.lib()
+    c1, c2, w0 = (ctypes.c_double() for _ in range(3))
+    for pp, ee in zip(po, eo):
+        L.speigen_stage_constants(pp, ee, ctypes.byref(c1), ctypes.byref(c2), ctypes.byref(w0))
+        r1, r2, r0 = o.stage_constants(pp, ee)
+        assert np.isclose(c1.value, r1, rtol=1e-15) and np.isclose(c2.value, r2, rtol=1e-15) and np.isclose(w0.value, r0, rtol=1e-15)
+
+
+@pytest.mark.parametrize("n,parts", [(50000, 8), (50000, 1), (10, 4), (7, 8), (200000, 3)])
+def test_shard_ranges_partition(n, parts):
+    prev = 0
+    sizes = []
+    for r in range(parts):
+        lo, hi = sb.shard_range(n, parts, r)
+        assert lo == prev and hi >= lo
+        prev = hi
+        sizes.append(hi - lo)
+    assert prev == n
+    assert max(sizes) == -(-n // parts)            # equal blocks of ceil(n/parts): NCCL allgather needs equal counts
+
+
+def test_panel_pitch_and_ld():
+    for ncr in range(1, 65):
+        p = sb.panel_pitch(ncr)
+        assert p >= ncr and p % 8 == 4             # bank-conflict-free DMMA B-fragment reads, 32-byte aligned rows
+    L = sb.lib()
+    assert L.speigen_matrix_ld(50000) == 50000 and L.speigen_matrix_ld(50001) == 50016
+
+
+def test_python_wrapper_error_behaviour_without_gpu():
+    X = np.random.default_rng(0).standard_normal((15, 10))
+    with pytest.raises(sb.SpEigenError): sb.spEigen(X[:, 0], 3, 0.5, data=True)
+    Xna = X.copy(); Xna[0, 0] = np.nan
+    with pytest.raises(sb.SpEigenError): sb.spEigen(Xna, 3, 0.5, data=True)
+    with pytest.raises(sb.SpEigenError): sb.spEigen(X, None, 0.5, data=True)
+    with pytest.raises(sb.SpEigenError): sb.spEigen(X, 3, float("nan"), data=True)
+    for q in (-1, 0, 0.5):
+        with pytest.raises(sb.SpEigenError): sb.spEigen(X, q, 0.5, data=True)
+    with pytest.raises(sb.SpEigenError): sb.spEigen(X, 3, 0.0, data=True)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly (never route through the oracle)."""
+    if sb.lib().speigen_device_count() > 0:
+        pytest.skip("a GPU is present")
+    X = np.random.default_rng(0).standard_normal((15, 10))
+    with pytest.raises(sb.SpEigenError) as ei:
+        sb.spEigen(X, 3, 0.5, data=True)
+    assert ei.value.code == 22 and "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sparseeigen_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("# oracle", ""), f"{f} mentions the oracle"
