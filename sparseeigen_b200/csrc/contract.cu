@@ -19,6 +19,7 @@
 // Replaces: R/spEigen.R:177 (G), :136/:138 (X %*% V0) of the reference (base-R dgemm/zgemm).
 #include "contract.cuh"
 #include "../../include/speigen_b200.h"
+#include <cstdlib>
 
 namespace speigen {
 
@@ -49,8 +50,12 @@ __device__ __forceinline__ int cta_of_unit(int64_t u, int64_t total, int64_t nct
   return static_cast<int>(((u + 1) * nctas - 1) / total);
 }
 
-template <int NT>
+// NTF = n-tiles (8 columns) on the FP64 tensor pipe (DMMA), RF = leftover columns (0 or 4) done with DFMA:
+// both share one FP64 datapath on B200 (tools/microbench/fp64_concurrency.cu: 36.5 TFLOP/s combined), so padding
+// q = 20 to 24 DMMA columns would waste 17 % of the binding resource; the hybrid issues exactly 20 columns of work.
+template <int NTF, int RF>
 __global__ void __launch_bounds__(kThreads, 1) k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
+  constexpr int NT = NTF + (RF > 0 ? 1 : 0);   // fragment tiles carried through fix-up / epilogue
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
@@ -119,6 +124,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_contract_std(const __grid_const
   for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  double facc[kMT][RF > 0 ? RF : 1];             // DFMA partial sums: this lane's k-slice of columns 8*NTF..8*NTF+RF-1
+#pragma unroll
+  for (int mt = 0; mt < kMT; ++mt)
+#pragma unroll
+    for (int c = 0; c < (RF > 0 ? RF : 1); ++c) facc[mt][c] = 0.0;
 
   // per-thread constant parts of the swizzled A addresses
   uint32_t a_row_off[kMT];
@@ -144,17 +154,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_contract_std(const __grid_const
       for (int k4 = 0; k4 < 4; ++k4) {
         const int il = b * 16 + k4 * 4 + kk;         // row of the staged panel tile
         const int chunk = (k4 * 4 + kk) >> 1;        // 16-byte chunk inside the 128-byte box row
-        double bf[NT];
+        double bf[NTF > 0 ? NTF : 1];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) bf[nt] = sU[il * pitch + nt * 8 + grp];
+        for (int nt = 0; nt < NTF; ++nt) bf[nt] = sU[il * pitch + nt * 8 + grp];
+        double uf[RF > 0 ? RF : 1];
+        if (RF > 0) {
+#pragma unroll
+          for (int c = 0; c < RF; c += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(sU + il * pitch + NTF * 8 + c);
+            uf[c] = t.x;
+            uf[c + 1] = t.y;
+          }
+        }
         double af[kMT];
 #pragma unroll
         for (int mt = 0; mt < kMT; ++mt)
           af[mt] = *reinterpret_cast<const double*>(sA + b * kBoxBytes + a_row_off[mt] + ((chunk ^ a_row7[mt]) << 4));
 #pragma unroll
-        for (int mt = 0; mt < kMT; ++mt)
+        for (int mt = 0; mt < kMT; ++mt) {
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) dmma_884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+          for (int nt = 0; nt < NTF; ++nt) dmma_884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+          if (RF > 0) {
+#pragma unroll
+            for (int c = 0; c < RF; ++c) facc[mt][c] = fma(af[mt], uf[c], facc[mt][c]);
+          }
+        }
       }
     }
     __syncwarp();
@@ -165,6 +189,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_contract_std(const __grid_const
     if (!seg_end) continue;
 
     // ---------------- end of this CTA's segment of row tile rt ----------------
+    if (RF > 0) {
+      // quad butterfly over the 4 k-lanes (fixed order), then lane kk keeps columns 2kk, 2kk+1 of the DFMA tile
+#pragma unroll
+      for (int mt = 0; mt < kMT; ++mt) {
+        double t[RF > 0 ? RF : 1];
+#pragma unroll
+        for (int c = 0; c < RF; ++c) {
+          double v = facc[mt][c];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          t[c] = v;
+          facc[mt][c] = 0.0;
+        }
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < RF; c += 2) {
+          if (kk == (c >> 1)) { c0 = t[c]; c1 = t[c + 1]; }
+        }
+        acc[mt][NT - 1][0] = c0;
+        acc[mt][NT - 1][1] = c1;
+      }
+    }
     const int64_t t_first = static_cast<int64_t>(rt) * prm.ksteps;
     const int c_first = cta_of_unit(t_first, prm.total_units, nctas);
     const int c_last = cta_of_unit(t_first + prm.ksteps - 1, prm.total_units, nctas);
@@ -496,18 +542,24 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// SPEIGEN_FORCE_DMMA=1 pads the leftover columns onto the tensor pipe instead (A/B measurement switch)
+inline bool prm_force_dmma() {
+  static const bool v = [] { const char* e = getenv("SPEIGEN_FORCE_DMMA"); return e && e[0] == '1'; }();
+  return v;
+}
+
 constexpr size_t kMaxDynSmem = 232448 - 8192;   // 227 KB per CTA minus (generous) static shared memory
 
 inline uint32_t round_up_u32(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
-template <int NT>
+template <int NTF, int RF>
 int launch_std_nt(const StreamMat& A, const KParams& prm, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    SPE_CUDA(cudaFuncSetAttribute(k_contract_std<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SPE_CUDA(cudaFuncSetAttribute(k_contract_std<NTF, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     attr_set = true;
   }
-  k_contract_std<NT><<<grid, kThreads, smem, stream>>>(A.tmap, prm);
+  k_contract_std<NTF, RF><<<grid, kThreads, smem, stream>>>(A.tmap, prm);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;
@@ -607,16 +659,29 @@ int launch_contract_std(const StreamMat& A, const double* P, int ncr, const EpiA
     return SPEIGEN_ERR_ARG;
   }
   const size_t smem = static_cast<size_t>(prm.stages) * prm.stage_bytes;
-  const int nt = (ncr + 7) / 8;
-  switch (nt) {
-    case 1: return launch_std_nt<1>(A, prm, grid, smem, stream);
-    case 2: return launch_std_nt<2>(A, prm, grid, smem, stream);
-    case 3: return launch_std_nt<3>(A, prm, grid, smem, stream);
-    case 4: return launch_std_nt<4>(A, prm, grid, smem, stream);
-    case 5: return launch_std_nt<5>(A, prm, grid, smem, stream);
-    case 6: return launch_std_nt<6>(A, prm, grid, smem, stream);
-    case 7: return launch_std_nt<7>(A, prm, grid, smem, stream);
-    default: return launch_std_nt<8>(A, prm, grid, smem, stream);
+  // columns: ntf full DMMA n-tiles + (remainder 1..4 -> 4 DFMA columns | remainder 5..7 -> one more padded DMMA tile)
+  int ntf = ncr / 8;
+  const int rem = ncr % 8;
+  int rf = 0;
+  if (rem >= 1 && rem <= 4 && !prm_force_dmma()) rf = 4;
+  else if (rem > 0) ntf += 1;
+  switch (ntf * 8 + rf) {
+    case 0 * 8 + 4: return launch_std_nt<0, 4>(A, prm, grid, smem, stream);
+    case 1 * 8 + 0: return launch_std_nt<1, 0>(A, prm, grid, smem, stream);
+    case 1 * 8 + 4: return launch_std_nt<1, 4>(A, prm, grid, smem, stream);
+    case 2 * 8 + 0: return launch_std_nt<2, 0>(A, prm, grid, smem, stream);
+    case 2 * 8 + 4: return launch_std_nt<2, 4>(A, prm, grid, smem, stream);
+    case 3 * 8 + 0: return launch_std_nt<3, 0>(A, prm, grid, smem, stream);
+    case 3 * 8 + 4: return launch_std_nt<3, 4>(A, prm, grid, smem, stream);
+    case 4 * 8 + 0: return launch_std_nt<4, 0>(A, prm, grid, smem, stream);
+    case 4 * 8 + 4: return launch_std_nt<4, 4>(A, prm, grid, smem, stream);
+    case 5 * 8 + 0: return launch_std_nt<5, 0>(A, prm, grid, smem, stream);
+    case 5 * 8 + 4: return launch_std_nt<5, 4>(A, prm, grid, smem, stream);
+    case 6 * 8 + 0: return launch_std_nt<6, 0>(A, prm, grid, smem, stream);
+    case 6 * 8 + 4: return launch_std_nt<6, 4>(A, prm, grid, smem, stream);
+    case 7 * 8 + 0: return launch_std_nt<7, 0>(A, prm, grid, smem, stream);
+    case 7 * 8 + 4: return launch_std_nt<7, 4>(A, prm, grid, smem, stream);
+    default: return launch_std_nt<8, 0>(A, prm, grid, smem, stream);
   }
 }
 
