@@ -223,8 +223,9 @@ def spEigen(X, q=1, rho=0.5, data=False, d=None, V=None, thres=1e-9, *, n_gpus=1
     nrow, m = X.shape
     if m == 1:
         raise SpEigenError(1, "Data is univariate!")                                   # :52
-    if _is_na(q) or _is_na(rho) or np.isnan(X).any():
+    if _is_na(q) or _is_na(rho):
         raise SpEigenError(2, "This function cannot handle NAs.")                      # :53
+    # anyNA(X) (:53) is evaluated by the device scan in speigen_solver_prepare (one streamed pass, no host copy)
     L = lib()
     _check(L.speigen_validate_args(nrow, m, float(q), float(rho)))                     # :54-55
     q = int(q)

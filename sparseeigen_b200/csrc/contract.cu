@@ -554,7 +554,10 @@ inline uint32_t round_up_u32(uint32_t x, uint32_t a) { return (x + a - 1) / a * 
 
 template <int NTF, int RF>
 int launch_std_nt(const StreamMat& A, const KParams& prm, int grid, size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];   // function attributes are per device
   if (!attr_set) {
     SPE_CUDA(cudaFuncSetAttribute(k_contract_std<NTF, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     attr_set = true;
@@ -566,7 +569,10 @@ int launch_std_nt(const StreamMat& A, const KParams& prm, int grid, size_t smem,
 }
 template <int NT>
 int launch_tr_nt(const StreamMat& A, const KParamsTr& prm, int grid, size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];   // function attributes are per device
   if (!attr_set) {
     SPE_CUDA(cudaFuncSetAttribute(k_contract_tr<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     attr_set = true;

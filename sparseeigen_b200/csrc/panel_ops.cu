@@ -768,11 +768,17 @@ template <int OP>
 int launch_produce(const PanelDims& pd, const ProdArgs& pa, cudaStream_t st) {
   const size_t smem = produce_smem(pd, OP);
   if (pd.cplx) {
-    static bool set = false;
+    static bool set_dev[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& set = set_dev[dev_ & 63];
     if (!set) { SPE_CUDA(cudaFuncSetAttribute(k_produce<OP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
     k_produce<OP, true><<<kPanelBlocks, kPT, smem, st>>>(pa);
   } else {
-    static bool set = false;
+    static bool set_dev[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& set = set_dev[dev_ & 63];
     if (!set) { SPE_CUDA(cudaFuncSetAttribute(k_produce<OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
     k_produce<OP, false><<<kPanelBlocks, kPT, smem, st>>>(pa);
   }
@@ -809,11 +815,17 @@ int launch_small(const PanelDims& pd, const double* gram_part, int nparts, int m
   if (threads > 1024) threads = 1024;
   const size_t smem = (2 * static_cast<size_t>(q) * q * (pd.cplx ? 2 : 1) + q) * sizeof(double) + q * sizeof(int) + 16;
   if (pd.cplx) {
-    static bool set = false;
+    static bool set_dev[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& set = set_dev[dev_ & 63];
     if (!set) { SPE_CUDA(cudaFuncSetAttribute(k_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
     k_small<true><<<1, threads, smem, st>>>(gram_part, nparts, q, mode, Msmall, evals, status);
   } else {
-    static bool set = false;
+    static bool set_dev[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& set = set_dev[dev_ & 63];
     if (!set) { SPE_CUDA(cudaFuncSetAttribute(k_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
     k_small<false><<<1, threads, smem, st>>>(gram_part, nparts, q, mode, Msmall, evals, status);
   }

@@ -275,6 +275,11 @@ int Solver::load_host(const double* X) {
                                  cudaMemcpyHostToDevice, d.st));
     } else {
       // S is m x m column-major and Hermitian: row j of A = column lo+j of S
+      if (d.a_ld == m * e) {   // no pitch padding: one contiguous DMA
+        SPE_CUDA(cudaMemcpyAsync(d.A, X + d.lo * m * e, static_cast<size_t>(d.hi - d.lo) * m * e * sizeof(double),
+                                 cudaMemcpyHostToDevice, d.st));
+        continue;
+      }
       SPE_CUDA(cudaMemcpy2DAsync(d.A, d.a_ld * sizeof(double), X + d.lo * m * e, static_cast<size_t>(m) * e * sizeof(double),
                                  static_cast<size_t>(m) * e * sizeof(double), static_cast<size_t>(d.hi - d.lo),
                                  cudaMemcpyHostToDevice, d.st));
