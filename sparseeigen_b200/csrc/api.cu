@@ -243,10 +243,19 @@ int speigen_solver_eig_small(speigen_solver* s, const double* C_host, int32_t nn
   if (nn < 1 || nn > S.bq) { set_error("eig_small: n %d outside 1..%d", nn, S.bq); return SPEIGEN_ERR_ARG; }
   const int e = 1 + S.cplx;
   const PanelDims pd = make_dims(S.m, nn, S.cplx);
-  std::vector<double> rm(static_cast<size_t>(nn) * nn * e), wm(static_cast<size_t>(nn) * nn * e);
+  const int ncr = nn * e;
+  // one "partial" in the real-Gram layout k_small sums: C[a][b] = (R[2a][2b] + R[2a+1][2b+1]) + i (R[2a][2b+1] - R[2a+1][2b])
+  std::vector<double> rm(static_cast<size_t>(ncr) * ncr, 0.0), wm(static_cast<size_t>(ncr) * ncr);
   for (int a = 0; a < nn; ++a)
-    for (int b = 0; b < nn; ++b)
-      for (int k = 0; k < e; ++k) rm[(static_cast<size_t>(a) * nn + b) * e + k] = C_host[(static_cast<size_t>(b) * nn + a) * e + k];
+    for (int b = 0; b < nn; ++b) {
+      const double* src = C_host + (static_cast<size_t>(b) * nn + a) * e;   // column-major input
+      if (S.cplx) {
+        rm[static_cast<size_t>(2 * a) * ncr + 2 * b] = src[0];
+        rm[static_cast<size_t>(2 * a) * ncr + 2 * b + 1] = src[1];
+      } else {
+        rm[static_cast<size_t>(a) * ncr + b] = src[0];
+      }
+    }
   Dev& d = S.devs[0];
   cudaSetDevice(d.ordinal);
   SPE_CUDA(cudaMemcpyAsync(d.ps.gram_part, rm.data(), rm.size() * sizeof(double), cudaMemcpyHostToDevice, d.st));
@@ -254,9 +263,16 @@ int speigen_solver_eig_small(speigen_solver* s, const double* C_host, int32_t nn
   SPE_CUDA(cudaMemcpyAsync(wm.data(), d.Msmall, wm.size() * sizeof(double), cudaMemcpyDeviceToHost, d.st));
   SPE_CUDA(cudaMemcpyAsync(evals, d.evals, nn * sizeof(double), cudaMemcpyDeviceToHost, d.st));
   SPE_CUDA(cudaStreamSynchronize(d.st));
-  for (int a = 0; a < nn; ++a)
-    for (int b = 0; b < nn; ++b)
-      for (int k = 0; k < e; ++k) W_host[(static_cast<size_t>(b) * nn + a) * e + k] = wm[(static_cast<size_t>(a) * nn + b) * e + k];
+  for (int a = 0; a < nn; ++a)          // hat form -> column-major (complex) eigenvectors
+    for (int b = 0; b < nn; ++b) {
+      double* dst = W_host + (static_cast<size_t>(b) * nn + a) * e;
+      if (S.cplx) {
+        dst[0] = wm[static_cast<size_t>(2 * a) * ncr + 2 * b];
+        dst[1] = wm[static_cast<size_t>(2 * a) * ncr + 2 * b + 1];
+      } else {
+        dst[0] = wm[static_cast<size_t>(a) * ncr + b];
+      }
+    }
   return SPEIGEN_OK;
 }
 

@@ -3,6 +3,7 @@
 #include "panel_ops.cuh"
 #include "../../include/speigen_b200.h"
 #include <cfloat>
+#include <algorithm>
 
 namespace speigen {
 namespace {
@@ -32,208 +33,267 @@ __device__ __forceinline__ bool last_block_done(int* ticket) {
   return s_is_last != 0;
 }
 
-// load `nrows` rows starting at r0 of a pitched panel into a shared tile (rows beyond r1 zero-filled)
-__device__ __forceinline__ void load_tile(double* tile, const double* P, int64_t r0, int64_t r1, int pitch) {
-  const int n = kTileRows * pitch;
-  const int64_t avail = (r1 - r0) * pitch;
-  const double* src = P + r0 * pitch;
-  for (int i = threadIdx.x; i < n; i += kPT) tile[i] = (i < avail) ? __ldcg(src + i) : 0.0;
-}
-
-// accumulate Gram entries of conj(TA)^T * TB over the tile rows (fixed row order)
-template <bool CPLX>
-__device__ __forceinline__ void gram_accumulate(double* gacc, const double* TA, const double* TB, int q, int pitch,
-                                                int nrows) {
-  const int nent = q * q;
-  if (CPLX) {
+// fixed-order sum of `n` partials spaced `stride` apart with 8 independent chains (ILP hides the L2 latency;
+// the combination order is fixed, so the result is bit-reproducible)
+__device__ __forceinline__ double sum_parts_ilp(const double* p, int n, size_t stride) {
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int k = 0;
+  for (; k + 8 <= n; k += 8) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int e = threadIdx.x + k * kPT;
-      if (e < nent) {
-        const int a = e / q, b = e - a * q;
-        double sr = gacc[2 * k], si = gacc[2 * k + 1];
-        for (int r = 0; r < nrows; ++r) {
-          const double ar = TA[r * pitch + 2 * a], ai = TA[r * pitch + 2 * a + 1];
-          const double br = TB[r * pitch + 2 * b], bi = TB[r * pitch + 2 * b + 1];
-          sr += ar * br + ai * bi;
-          si += ar * bi - ai * br;
-        }
-        gacc[2 * k] = sr;
-        gacc[2 * k + 1] = si;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int e = threadIdx.x + k * kPT;
-      if (e < nent) {
-        const int a = e / q, b = e - a * q;
-        double s = gacc[k];
-        for (int r = 0; r < nrows; ++r) s += TA[r * pitch + a] * TB[r * pitch + b];
-        gacc[k] = s;
-      }
-    }
+    for (int u = 0; u < 8; ++u) s[u] += __ldcg(p + static_cast<size_t>(k + u) * stride);
   }
+  for (int u = 0; k < n; ++k, ++u) s[u] += __ldcg(p + static_cast<size_t>(k) * stride);
+  return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
-template <bool CPLX>
-__device__ __forceinline__ void gram_store(const double* gacc, double* gram_part, int q) {
-  const int nent = q * q;
-  if (CPLX) {
-    double* dst = gram_part + static_cast<size_t>(blockIdx.x) * nent * 2;
+__device__ __forceinline__ double min_parts_ilp(const double* p, int n, size_t stride) {
+  double s[4] = {DBL_MAX, DBL_MAX, DBL_MAX, DBL_MAX};
+  int k = 0;
+  for (; k + 4 <= n; k += 4) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int e = threadIdx.x + k * kPT;
-      if (e < nent) { dst[2 * e] = gacc[2 * k]; dst[2 * e + 1] = gacc[2 * k + 1]; }
-    }
-  } else {
-    double* dst = gram_part + static_cast<size_t>(blockIdx.x) * nent;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int e = threadIdx.x + k * kPT;
-      if (e < nent) dst[e] = gacc[k];
-    }
+    for (int u = 0; u < 4; ++u) s[u] = fmin(s[u], __ldcg(p + static_cast<size_t>(k + u) * stride));
   }
+  for (; k < n; ++k) s[0] = fmin(s[0], __ldcg(p + static_cast<size_t>(k) * stride));
+  return fmin(fmin(s[0], s[1]), fmin(s[2], s[3]));
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool CPLX>
-__global__ void __launch_bounds__(kPT) k_gram(const double* A, const double* B, int64_t m, int q, int pitch,
-                                              double* gram_part) {
-  extern __shared__ double sm[];
-  double* TA = sm;
-  double* TB = (A == B) ? TA : sm + kTileRows * pitch;
+// Real Gram partials R = A'^T B' of the real views (ncr columns) with FP64 tensor-core MMAs, fragments
+// read straight from the L2-resident panels.  Complex Gram entries are recombined in k_small:
+//   C[a][b] = (R[2a][2b] + R[2a+1][2b+1]) + i (R[2a][2b+1] - R[2a+1][2b]).
+// Block b owns a fixed row range, warp w the 4-row chunks w, w+8, ...; warps are summed in order.
+// ------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(kPT) k_gram_mma(const double* A, const double* B, int64_t m, int ncr, int pitch,
+                                                  double* gram_part) {
+  __shared__ double s_acc[NB * NB * 64];
   int64_t r0, r1;
   block_rows(m, r0, r1);
-  double gacc[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 2, kk = lane & 3;
+  const int ntiles = (ncr + 7) / 8;
+  const int64_t nchunks = (r1 - r0 + 3) / 4;
+  const bool same = (A == B);
+  double* out = gram_part + static_cast<size_t>(blockIdx.x) * ncr * ncr;
+  for (int tm0 = 0; tm0 < ntiles; tm0 += NB) {
+    for (int tn0 = 0; tn0 < ntiles; tn0 += NB) {
+      double acc[NB][NB][2];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) gacc[k] = 0.0;
-  for (int64_t t = r0; t < r1; t += kTileRows) {
-    load_tile(TA, A, t, r1, pitch);
-    if (A != B) load_tile(TB, B, t, r1, pitch);
-    __syncthreads();
-    const int nrows = static_cast<int>((r1 - t) < kTileRows ? (r1 - t) : kTileRows);
-    gram_accumulate<CPLX>(gacc, TA, TB, q, pitch, nrows);
-    __syncthreads();
+      for (int i = 0; i < NB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int64_t ch = warp; ch < nchunks; ch += kPT / 32) {
+        const int64_t row = r0 + ch * 4 + kk;
+        const bool rok = row < r1;
+        double af[NB], bf[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          const int ca = (tm0 + i) * 8 + grp, cb = (tn0 + i) * 8 + grp;
+          af[i] = (rok && ca < ncr) ? __ldcg(A + row * pitch + ca) : 0.0;
+          bf[i] = (same && tm0 == tn0) ? af[i] : ((rok && cb < ncr) ? __ldcg(B + row * pitch + cb) : 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+      // fixed-order reduction over the 8 warps
+      for (int w = 0; w < kPT / 32; ++w) {
+        if (warp == w) {
+#pragma unroll
+          for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              double* d = s_acc + (i * NB + j) * 64 + lane * 2;
+              if (w == 0) { d[0] = acc[i][j][0]; d[1] = acc[i][j][1]; }
+              else { d[0] += acc[i][j][0]; d[1] += acc[i][j][1]; }
+            }
+        }
+        __syncthreads();
+      }
+      for (int idx = threadIdx.x; idx < NB * NB * 64; idx += kPT) {
+        const int t = idx >> 6, l = (idx & 63) >> 1, e = idx & 1;
+        const int i = t / NB, j = t - i * NB;
+        const int a = (tm0 + i) * 8 + (l >> 2), c = (tn0 + j) * 8 + 2 * (l & 3) + e;
+        if (a < ncr && c < ncr) out[static_cast<size_t>(a) * ncr + c] = s_acc[idx];
+      }
+      __syncthreads();
+    }
   }
-  gram_store<CPLX>(gacc, gram_part, q);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Producer kernels: Out tile = op(inputs); fused Gram / min|.| stage-1 reductions of Out.
-enum ProdOp { OP_APPLY = 0, OP_REWEIGHT = 1, OP_EXTRAP = 2 };
-struct ProdArgs {
-  const double* in0;
-  const double* in1;
-  const double* in2;
-  const double* Msmall;
-  const double* d;
-  const double* rho;
-  const double* wmax;
-  StageConsts sc;
-  double a;
+// Out = A * Mh  (Mh: real ncr x ncr "hat" form of the small matrix, produced by k_small) with DMMA; optional fused
+// stage-1 reductions of Out: real Gram partials (NT <= 5) and column min|.| partials.  In-place safe.
+// ------------------------------------------------------------------------------------------------
+struct ApplyArgs {
+  const double* A;
+  const double* Mh;
   double* Out;
   double* gram_part;
   double* absmin_part;
   int64_t m;
-  int q, ncr, pitch;
+  int q, ncr, pitch, cplx;
 };
 
-template <int OP, bool CPLX>
-__global__ void __launch_bounds__(kPT) k_produce(const ProdArgs p) {
+template <int NT, bool GRAM>
+__global__ void __launch_bounds__(kPT) k_apply_mma(const ApplyArgs p) {
   extern __shared__ double sm[];
-  const int pitch = p.pitch, q = p.q, ncr = p.ncr;
-  double* Tin = sm;                              // [kTileRows][pitch]  (APPLY input)
-  double* Tout = sm + kTileRows * pitch;         // [kTileRows][pitch]
-  double* Ms = Tout + kTileRows * pitch;         // APPLY: q*q*(1+CPLX) ; REWEIGHT: d,rho,wmax
-  if (OP == OP_APPLY) {
-    const int n = q * q * (CPLX ? 2 : 1);
-    for (int i = threadIdx.x; i < n; i += kPT) Ms[i] = p.Msmall[i];
-  } else if (OP == OP_REWEIGHT) {
-    for (int i = threadIdx.x; i < q; i += kPT) { Ms[i] = p.d[i]; Ms[kMaxCols + i] = p.rho[i]; Ms[2 * kMaxCols + i] = p.wmax[i]; }
+  const int ncr = p.ncr, pitch = p.pitch;
+  const int kt = (ncr + 3) / 4;                 // k4 steps
+  const int pm = panel_pitch(NT * 8);           // conflict-free pitch of the staged small matrix
+  double* Ms = sm;                              // [kt*4][pm]
+  double* tiles = Ms + kt * 4 * pm;             // per-warp [8][pm] staging for the fused Gram
+  __shared__ double s_min[kPT / 32][kMaxCols];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 2, kk = lane & 3;
+  for (int idx = threadIdx.x; idx < kt * 4 * pm; idx += kPT) {
+    const int k = idx / pm, c = idx - k * pm;
+    Ms[idx] = (k < ncr && c < ncr) ? p.Mh[static_cast<size_t>(k) * ncr + c] : 0.0;
   }
   int64_t r0, r1;
   block_rows(p.m, r0, r1);
-  double gacc[16];
+  const int64_t ntile = (r1 - r0 + 7) / 8;
+  double gacc[GRAM ? NT : 1][GRAM ? NT : 1][2];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) gacc[k] = 0.0;
-  double amin = DBL_MAX;
+  for (int i = 0; i < (GRAM ? NT : 1); ++i)
+#pragma unroll
+    for (int j = 0; j < (GRAM ? NT : 1); ++j) gacc[i][j][0] = gacc[i][j][1] = 0.0;
+  double amin[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) amin[nt][0] = amin[nt][1] = DBL_MAX;
   __syncthreads();
-  for (int64_t t = r0; t < r1; t += kTileRows) {
-    const int nrows = static_cast<int>((r1 - t) < kTileRows ? (r1 - t) : kTileRows);
-    if (OP == OP_APPLY) {
-      load_tile(Tin, p.in0, t, r1, pitch);
-      __syncthreads();
-      const int nout = nrows * q;
-      for (int idx = threadIdx.x; idx < nout; idx += kPT) {
-        const int r = idx / q, c = idx - r * q;
-        if (CPLX) {
-          double sr = 0.0, si = 0.0;
-          for (int a = 0; a < q; ++a) {
-            const double ar = Tin[r * pitch + 2 * a], ai = Tin[r * pitch + 2 * a + 1];
-            const double mr = Ms[(a * q + c) * 2], mi = Ms[(a * q + c) * 2 + 1];
-            sr += ar * mr - ai * mi;
-            si += ar * mi + ai * mr;
-          }
-          Tout[r * pitch + 2 * c] = sr;
-          Tout[r * pitch + 2 * c + 1] = si;
-        } else {
-          double s = 0.0;
-          for (int a = 0; a < q; ++a) s += Tin[r * pitch + a] * Ms[a * q + c];
-          Tout[r * pitch + c] = s;
+  double* mytile = tiles + warp * 8 * pm;
+  for (int64_t t = warp; t < ntile; t += kPT / 32) {
+    const int64_t row = r0 + t * 8 + grp;
+    const bool rok = row < r1;
+    double acc[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+    for (int k4 = 0; k4 < kt; ++k4) {
+      const int k = k4 * 4 + kk;
+      const double af = (rok && k < ncr) ? __ldcg(p.A + row * pitch + k) : 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) dmma_884(acc[nt][0], acc[nt][1], af, Ms[k * pm + nt * 8 + grp]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int c0 = nt * 8 + 2 * kk;
+      if (rok && c0 < ncr) {
+        if (c0 + 1 < ncr) *reinterpret_cast<double2*>(p.Out + row * pitch + c0) = make_double2(acc[nt][0], acc[nt][1]);
+        else p.Out[row * pitch + c0] = acc[nt][0];
+        if (p.absmin_part) {
+          if (p.cplx) amin[nt][0] = fmin(amin[nt][0], hypot(acc[nt][0], acc[nt][1]));
+          else { amin[nt][0] = fmin(amin[nt][0], fabs(acc[nt][0])); if (c0 + 1 < ncr) amin[nt][1] = fmin(amin[nt][1], fabs(acc[nt][1])); }
         }
       }
-    } else if (OP == OP_REWEIGHT) {
-      // B = d*Y - (w(|V|) - wmax) * V * rho     (R/spEigen.R:170-177)
-      const int nout = nrows * q;
-      for (int idx = threadIdx.x; idx < nout; idx += kPT) {
-        const int r = idx / q, c = idx - r * q;
-        const size_t g = static_cast<size_t>(t + r) * pitch;
-        if (CPLX) {
-          const double vr = __ldcg(p.in1 + g + 2 * c), vi = __ldcg(p.in1 + g + 2 * c + 1);
-          const double yr = __ldcg(p.in0 + g + 2 * c), yi = __ldcg(p.in0 + g + 2 * c + 1);
-          const double tt = weight_of_abs(hypot(vr, vi), p.sc) - Ms[2 * kMaxCols + c];
-          Tout[r * pitch + 2 * c] = Ms[c] * yr - tt * vr * Ms[kMaxCols + c];
-          Tout[r * pitch + 2 * c + 1] = Ms[c] * yi - tt * vi * Ms[kMaxCols + c];
-        } else {
-          const double v = __ldcg(p.in1 + g + c), y = __ldcg(p.in0 + g + c);
-          const double tt = weight_of_abs(fabs(v), p.sc) - Ms[2 * kMaxCols + c];
-          Tout[r * pitch + c] = Ms[c] * y - tt * v * Ms[kMaxCols + c];
-        }
-      }
-    } else {
-      // V0 = V - 2 a R + a^2 U      (R/spEigen.R:121-127)
-      const int nout = nrows * ncr;
-      const double a = p.a, a2 = p.a * p.a;
-      for (int idx = threadIdx.x; idx < nout; idx += kPT) {
-        const int r = idx / ncr, c = idx - r * ncr;
-        const size_t g = static_cast<size_t>(t + r) * pitch + c;
-        const double v = __ldcg(p.in0 + g), v1 = __ldcg(p.in1 + g), v2 = __ldcg(p.in2 + g);
-        const double R = v1 - v;
-        const double U = v2 - v1 - R;
-        Tout[r * pitch + c] = v - 2.0 * a * R + a2 * U;
+      if (GRAM) {   // stage the 8 x ncr output tile (zeros outside) for the Gram fragments
+        const bool ok = rok && c0 < ncr;
+        mytile[grp * pm + c0] = ok ? acc[nt][0] : 0.0;
+        mytile[grp * pm + c0 + 1] = (ok && c0 + 1 < ncr) ? acc[nt][1] : 0.0;
       }
     }
-    __syncthreads();
-    // write the tile
-    {
-      const int nout = nrows * ncr;
-      for (int idx = threadIdx.x; idx < nout; idx += kPT) {
-        const int r = idx / ncr, c = idx - r * ncr;
-        p.Out[static_cast<size_t>(t + r) * pitch + c] = Tout[r * pitch + c];
+    if (GRAM) {
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double f[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) f[i] = mytile[(h * 4 + kk) * pm + i * 8 + grp];
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) dmma_884(gacc[i][j][0], gacc[i][j][1], f[i], f[j]);
       }
+      __syncwarp();
     }
-    if (p.gram_part) gram_accumulate<CPLX>(gacc, Tout, Tout, q, pitch, nrows);
-    if (p.absmin_part && threadIdx.x < q) {
-      const int c = threadIdx.x;
-      for (int r = 0; r < nrows; ++r) {
-        const double v = CPLX ? hypot(Tout[r * pitch + 2 * c], Tout[r * pitch + 2 * c + 1]) : fabs(Tout[r * pitch + c]);
-        amin = fmin(amin, v);
-      }
-    }
-    __syncthreads();
   }
-  if (p.gram_part) gram_store<CPLX>(gacc, p.gram_part, q);
-  if (p.absmin_part && threadIdx.x < q) p.absmin_part[static_cast<size_t>(blockIdx.x) * kMaxCols + threadIdx.x] = amin;
+  if (p.absmin_part) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = amin[nt][e];
+        v = fmin(v, __shfl_xor_sync(0xffffffffu, v, 4));
+        v = fmin(v, __shfl_xor_sync(0xffffffffu, v, 8));
+        v = fmin(v, __shfl_xor_sync(0xffffffffu, v, 16));
+        if (grp == 0 && nt * 8 + 2 * kk + e < kMaxCols) s_min[warp][nt * 8 + 2 * kk + e] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < p.q) {
+      const int col = p.cplx ? 2 * threadIdx.x : threadIdx.x;
+      double v = s_min[0][col];
+      for (int w = 1; w < kPT / 32; ++w) v = fmin(v, s_min[w][col]);
+      p.absmin_part[static_cast<size_t>(blockIdx.x) * kMaxCols + threadIdx.x] = v;
+    }
+  }
+  if (GRAM) {
+    __syncthreads();
+    double* s_acc = tiles;   // reuse the staging area: NT*NT*64 doubles <= 8 warps * 8 * pm
+    double* out = p.gram_part + static_cast<size_t>(blockIdx.x) * ncr * ncr;
+    for (int w = 0; w < kPT / 32; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            double* d = s_acc + (i * NT + j) * 64 + lane * 2;
+            if (w == 0) { d[0] = gacc[i][j][0]; d[1] = gacc[i][j][1]; }
+            else { d[0] += gacc[i][j][0]; d[1] += gacc[i][j][1]; }
+          }
+      }
+      __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < NT * NT * 64; idx += kPT) {
+      const int t = idx >> 6, l = (idx & 63) >> 1, e = idx & 1;
+      const int i = t / NT, j = t - i * NT;
+      const int a = i * 8 + (l >> 2), c = j * 8 + 2 * (l & 3) + e;
+      if (a < ncr && c < ncr) out[static_cast<size_t>(a) * ncr + c] = s_acc[idx];
+    }
+  }
+}
+
+// ---- elementwise producers ---------------------------------------------------------------------------
+// B = d*Y - (w(|V|) - wmax) * V * rho     (R/spEigen.R:170-177)
+template <bool CPLX>
+__global__ void __launch_bounds__(256) k_reweight(const double* Y, const double* V, const double* d, const double* rho,
+                                                  const double* wmax, StageConsts sc, int64_t m, int q, int pitch,
+                                                  double* B) {
+  __shared__ double s_d[kMaxCols], s_rho[kMaxCols], s_w[kMaxCols];
+  if (threadIdx.x < q) { s_d[threadIdx.x] = d[threadIdx.x]; s_rho[threadIdx.x] = rho[threadIdx.x]; s_w[threadIdx.x] = wmax[threadIdx.x]; }
+  __syncthreads();
+  const int64_t n = m * q;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / q;
+    const int c = static_cast<int>(idx - r * q);
+    if (CPLX) {
+      const size_t g = static_cast<size_t>(r) * pitch + 2 * c;
+      const double2 v = *reinterpret_cast<const double2*>(V + g);
+      const double2 y = *reinterpret_cast<const double2*>(Y + g);
+      const double tt = weight_of_abs(hypot(v.x, v.y), sc) - s_w[c];
+      *reinterpret_cast<double2*>(B + g) = make_double2(s_d[c] * y.x - tt * v.x * s_rho[c], s_d[c] * y.y - tt * v.y * s_rho[c]);
+    } else {
+      const size_t g = static_cast<size_t>(r) * pitch + c;
+      const double v = V[g], y = Y[g];
+      const double tt = weight_of_abs(fabs(v), sc) - s_w[c];
+      B[g] = s_d[c] * y - tt * v * s_rho[c];
+    }
+  }
+}
+// V0 = V - 2 a R + a^2 U,  R = V1 - V, U = V2 - V1 - R      (R/spEigen.R:121-127)
+__global__ void __launch_bounds__(256) k_extrapolate(const double* V, const double* V1, const double* V2, double a,
+                                                     int64_t m, int ncr, int pitch, double* Out) {
+  const int64_t n = m * ncr;
+  const double a2 = a * a;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / ncr;
+    const size_t g = static_cast<size_t>(r) * pitch + (idx - r * ncr);
+    const double v = V[g], v1 = V1[g], v2 = V2[g];
+    const double R = v1 - v;
+    const double U = v2 - v1 - R;
+    Out[g] = v - 2.0 * a * R + a2 * U;
+  }
 }
 
 template <bool CPLX>
@@ -263,9 +323,7 @@ __global__ void __launch_bounds__(kPT) k_absmin(const double* V, int64_t m, int 
 __global__ void k_wmax(const double* absmin_part, int nparts, int q, StageConsts sc, double* wmax) {
   const int c = threadIdx.x;
   if (c >= q) return;
-  double amin = DBL_MAX;
-  for (int b = 0; b < nparts; ++b) amin = fmin(amin, absmin_part[static_cast<size_t>(b) * kMaxCols + c]);
-  wmax[c] = weight_of_abs(amin, sc);
+  wmax[c] = weight_of_abs(min_parts_ilp(absmin_part + c, nparts, kMaxCols), sc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -545,6 +603,21 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// write entry (a, c) = (mr + i mi) of the small matrix in the real "hat" form consumed by k_apply_mma:
+//   real: Mh[a][c] = mr ;  complex: [[mr, mi], [-mi, mr]] at rows 2a,2a+1 / columns 2c,2c+1
+template <bool CPLX>
+__device__ __forceinline__ void store_hat(double* Mh, int q, int a, int c, double mr, double mi) {
+  if (CPLX) {
+    const int n = 2 * q;
+    Mh[(2 * a) * n + 2 * c] = mr;
+    Mh[(2 * a) * n + 2 * c + 1] = mi;
+    Mh[(2 * a + 1) * n + 2 * c] = -mi;
+    Mh[(2 * a + 1) * n + 2 * c + 1] = mr;
+  } else {
+    Mh[a * q + c] = mr;
+  }
+}
+
 template <bool CPLX>
 __global__ void __launch_bounds__(1024) k_small(const double* gram_part, int nparts, int q, int mode, double* Msmall,
                                                 double* evals, int* status) {
@@ -558,22 +631,96 @@ __global__ void __launch_bounds__(1024) k_small(const double* gram_part, int npa
   const int tid = threadIdx.x, nth = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
 
-  // fixed-order sum of the stage-1 Gram partials; C[a][b] sits at part[(a*q+b)*E]
-  for (int e = tid; e < q * q; e += nth) {
-    const int a = e / q, b = e - a * q;
-    double sr = 0.0, si = 0.0;
-    for (int k = 0; k < nparts; ++k) {
-      const double* src = gram_part + (static_cast<size_t>(k) * q * q + e) * E;
-      sr += __ldcg(src);
-      if (CPLX) si += __ldcg(src + 1);
+  // fixed-order sum of the stage-1 real Gram partials R (ncr x ncr, ncr = q*E) and, for complex panels, the
+  // recombination C[a][b] = (R[2a][2b] + R[2a+1][2b+1]) + i (R[2a][2b+1] - R[2a+1][2b])
+  {
+    const int ncr = q * E;
+    const size_t pstride = static_cast<size_t>(ncr) * ncr;
+    for (int e = tid; e < q * q; e += nth) {
+      const int a = e / q, b = e - a * q;
+      double sr, si = 0.0;
+      if (CPLX) {
+        const double r00 = sum_parts_ilp(gram_part + static_cast<size_t>(2 * a) * ncr + 2 * b, nparts, pstride);
+        const double r11 = sum_parts_ilp(gram_part + static_cast<size_t>(2 * a + 1) * ncr + 2 * b + 1, nparts, pstride);
+        const double r01 = sum_parts_ilp(gram_part + static_cast<size_t>(2 * a) * ncr + 2 * b + 1, nparts, pstride);
+        const double r10 = sum_parts_ilp(gram_part + static_cast<size_t>(2 * a + 1) * ncr + 2 * b, nparts, pstride);
+        sr = r00 + r11;
+        si = r01 - r10;
+      } else {
+        sr = sum_parts_ilp(gram_part + static_cast<size_t>(a) * ncr + b, nparts, pstride);
+      }
+      F[(b * q + a) * E] = sr;
+      if (CPLX) F[(b * q + a) * E + 1] = si;
+      W[(b * q + a) * E] = (a == b) ? 1.0 : 0.0;
+      if (CPLX) W[(b * q + a) * E + 1] = 0.0;
     }
-    F[(b * q + a) * E] = sr;
-    if (CPLX) F[(b * q + a) * E + 1] = si;
-    W[(b * q + a) * E] = (a == b) ? 1.0 : 0.0;
-    if (CPLX) W[(b * q + a) * E + 1] = 0.0;
   }
   if (tid == 0) s_rot = 0;
   __syncthreads();
+
+  // Fast path (second polar pass): C = I + E with tiny E  =>  C^{-1/2} = I - E/2 + 3E^2/8 - 5E^3/16 + O(E^4).
+  // Taken when max|E| <= 1e-4 / q (truncation <= 0.3 (q max|E|)^4 <= 3e-17); otherwise the Jacobi solver below.
+  if (mode == SMALL_INVSQRT) {
+    __shared__ double s_emax[32];
+    double emax = 0.0;
+    for (int e = tid; e < q * q; e += nth) {
+      const int a = e / q, b = e - a * q;
+      const double re = F[(b * q + a) * E] - ((a == b) ? 1.0 : 0.0);
+      const double im = CPLX ? F[(b * q + a) * E + E - 1] : 0.0;
+      emax = fmax(emax, fmax(fabs(re), fabs(im)));
+    }
+    for (int o = 16; o; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    if (lane == 0) s_emax[warp] = emax;
+    __syncthreads();
+    emax = 0.0;
+    for (int w = 0; w < (nth >> 5); ++w) emax = fmax(emax, s_emax[w]);
+    if (emax * q <= 1e-4) {
+      // W <- E (column-major like F), lam-region unused; E2 goes to Msmall-sized scratch in F after use
+      for (int e = tid; e < q * q; e += nth) {
+        const int a = e / q, b = e - a * q;
+        W[(b * q + a) * E] = F[(b * q + a) * E] - ((a == b) ? 1.0 : 0.0);
+        if (CPLX) W[(b * q + a) * E + E - 1] = F[(b * q + a) * E + E - 1];
+      }
+      __syncthreads();
+      // F <- E^2
+      for (int e = tid; e < q * q; e += nth) {
+        const int a = e / q, b = e - a * q;
+        double sr = 0.0, si = 0.0;
+        for (int c = 0; c < q; ++c) {
+          const double xr = W[(c * q + a) * E], yr = W[(b * q + c) * E];
+          if (CPLX) {
+            const double xi = W[(c * q + a) * E + E - 1], yi = W[(b * q + c) * E + E - 1];
+            sr += xr * yr - xi * yi;
+            si += xr * yi + xi * yr;
+          } else {
+            sr += xr * yr;
+          }
+        }
+        F[(b * q + a) * E] = sr;
+        if (CPLX) F[(b * q + a) * E + E - 1] = si;
+      }
+      __syncthreads();
+      // M = I - E/2 + 3/8 E^2 - 5/16 E^3   (E^3 = E * E^2)
+      for (int e = tid; e < q * q; e += nth) {
+        const int a = e / q, b = e - a * q;
+        double sr = 0.0, si = 0.0;
+        for (int c = 0; c < q; ++c) {
+          const double xr = W[(c * q + a) * E], yr = F[(b * q + c) * E];
+          if (CPLX) {
+            const double xi = W[(c * q + a) * E + E - 1], yi = F[(b * q + c) * E + E - 1];
+            sr += xr * yr - xi * yi;
+            si += xr * yi + xi * yr;
+          } else {
+            sr += xr * yr;
+          }
+        }
+        const double mr = ((a == b) ? 1.0 : 0.0) - 0.5 * W[(b * q + a) * E] + 0.375 * F[(b * q + a) * E] - 0.3125 * sr;
+        const double mi = CPLX ? (-0.5 * W[(b * q + a) * E + E - 1] + 0.375 * F[(b * q + a) * E + E - 1] - 0.3125 * si) : 0.0;
+        store_hat<CPLX>(Msmall, q, a, b, mr, mi);
+      }
+      return;
+    }
+  }
 
   const int qe = q + (q & 1);
   const int npairs = qe / 2;
@@ -705,8 +852,7 @@ __global__ void __launch_bounds__(1024) k_small(const double* gram_part, int npa
           sr += lam[c] * war * wbr;
         }
       }
-      Msmall[e * E] = sr;
-      if (CPLX) Msmall[e * E + E - 1] = si;
+      store_hat<CPLX>(Msmall, q, a, b, sr, si);
     }
   } else {
     if (tid < q) {
@@ -719,8 +865,7 @@ __global__ void __launch_bounds__(1024) k_small(const double* gram_part, int npa
     for (int e = tid; e < q * q; e += nth) {
       const int a = e / q, c = e - a * q;
       const int rc = rank[c];
-      Msmall[(a * q + rc) * E] = W[(c * q + a) * E];
-      if (CPLX) Msmall[(a * q + rc) * E + E - 1] = W[(c * q + a) * E + E - 1];
+      store_hat<CPLX>(Msmall, q, a, rc, W[(c * q + a) * E], CPLX ? W[(c * q + a) * E + E - 1] : 0.0);
     }
   }
 }
@@ -757,50 +902,19 @@ __global__ void k_sum_parts(const double* parts, int nparts, int len, double* ou
   out[i] = s;
 }
 
-size_t produce_smem(const PanelDims& pd, int op) {
-  size_t n = 2 * static_cast<size_t>(kTileRows) * pd.pitch;
-  if (op == OP_APPLY) n += static_cast<size_t>(pd.q) * pd.q * (pd.cplx ? 2 : 1);
-  else n += 3 * kMaxCols;
-  return n * sizeof(double);
-}
-
-template <int OP>
-int launch_produce(const PanelDims& pd, const ProdArgs& pa, cudaStream_t st) {
-  const size_t smem = produce_smem(pd, OP);
-  if (pd.cplx) {
-    static bool set_dev[64] = {};
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    bool& set = set_dev[dev_ & 63];
-    if (!set) { SPE_CUDA(cudaFuncSetAttribute(k_produce<OP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
-    k_produce<OP, true><<<kPanelBlocks, kPT, smem, st>>>(pa);
-  } else {
-    static bool set_dev[64] = {};
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    bool& set = set_dev[dev_ & 63];
-    if (!set) { SPE_CUDA(cudaFuncSetAttribute(k_produce<OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
-    k_produce<OP, false><<<kPanelBlocks, kPT, smem, st>>>(pa);
-  }
-  SPE_CUDA(cudaGetLastError());
-  note_launch(1);
-  return SPEIGEN_OK;
-}
-
-ProdArgs base_args(const PanelDims& pd) {
-  ProdArgs pa{};
-  pa.m = pd.m; pa.q = pd.q; pa.ncr = pd.ncr; pa.pitch = pd.pitch;
-  return pa;
-}
-
 inline int nblk(int64_t n, int t = 256) { return static_cast<int>((n + t - 1) / t); }
 
 }  // namespace
 
 int launch_gram(const PanelDims& pd, const double* A, const double* B, double* gram_part, cudaStream_t st) {
-  const size_t smem = (A == B ? 1 : 2) * static_cast<size_t>(kTileRows) * pd.pitch * sizeof(double);
-  if (pd.cplx) k_gram<true><<<kPanelBlocks, kPT, smem, st>>>(A, B, pd.m, pd.q, pd.pitch, gram_part);
-  else k_gram<false><<<kPanelBlocks, kPT, smem, st>>>(A, B, pd.m, pd.q, pd.pitch, gram_part);
+  const int nt = (pd.ncr + 7) / 8;
+  switch (nt <= 5 ? nt : 4) {
+    case 1: k_gram_mma<1><<<kPanelBlocks, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
+    case 2: k_gram_mma<2><<<kPanelBlocks, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
+    case 3: k_gram_mma<3><<<kPanelBlocks, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
+    case 5: k_gram_mma<5><<<kPanelBlocks, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
+    default: k_gram_mma<4><<<kPanelBlocks, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
+  }
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;
@@ -834,25 +948,71 @@ int launch_small(const PanelDims& pd, const double* gram_part, int nparts, int m
   return SPEIGEN_OK;
 }
 
+template <int NT>
+static int launch_apply_nt(const ApplyArgs& pa, bool gram, cudaStream_t st) {
+  const int kt = (pa.ncr + 3) / 4;
+  const int pm = panel_pitch(NT * 8);
+  size_t smem = static_cast<size_t>(kt) * 4 * pm * sizeof(double);
+  if (gram) smem += std::max<size_t>(static_cast<size_t>(kPT / 32) * 8 * pm, static_cast<size_t>(NT) * NT * 64) * sizeof(double);
+  static bool set_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& set = set_dev[dev_ & 63];
+  if (!set) {
+    SPE_CUDA(cudaFuncSetAttribute(k_apply_mma<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    SPE_CUDA(cudaFuncSetAttribute(k_apply_mma<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    set = true;
+  }
+  if (gram) k_apply_mma<NT, true><<<kPanelBlocks, kPT, smem, st>>>(pa);
+  else k_apply_mma<NT, false><<<kPanelBlocks, kPT, smem, st>>>(pa);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+
 int launch_apply(const PanelDims& pd, const double* A, const double* Msmall, double* Out, double* gram_part_out,
                  double* absmin_part_out, cudaStream_t st) {
-  ProdArgs pa = base_args(pd);
-  pa.in0 = A; pa.Msmall = Msmall; pa.Out = Out; pa.gram_part = gram_part_out; pa.absmin_part = absmin_part_out;
-  return launch_produce<OP_APPLY>(pd, pa, st);
+  ApplyArgs pa{};
+  pa.A = A; pa.Mh = Msmall; pa.Out = Out; pa.absmin_part = absmin_part_out;
+  pa.m = pd.m; pa.q = pd.q; pa.ncr = pd.ncr; pa.pitch = pd.pitch; pa.cplx = pd.cplx;
+  const int nt = (pd.ncr + 7) / 8;
+  const bool fuse = gram_part_out != nullptr && nt <= 5;   // Gram accumulators fit in registers
+  pa.gram_part = fuse ? gram_part_out : nullptr;
+  int rc;
+  switch (nt) {
+    case 1: rc = launch_apply_nt<1>(pa, fuse, st); break;
+    case 2: rc = launch_apply_nt<2>(pa, fuse, st); break;
+    case 3: rc = launch_apply_nt<3>(pa, fuse, st); break;
+    case 4: rc = launch_apply_nt<4>(pa, fuse, st); break;
+    case 5: rc = launch_apply_nt<5>(pa, fuse, st); break;
+    case 6: rc = launch_apply_nt<6>(pa, false, st); break;
+    case 7: rc = launch_apply_nt<7>(pa, false, st); break;
+    default: rc = launch_apply_nt<8>(pa, false, st); break;
+  }
+  if (rc != SPEIGEN_OK) return rc;
+  if (gram_part_out && !fuse) return launch_gram(pd, Out, Out, gram_part_out, st);
+  return SPEIGEN_OK;
 }
 
 int launch_reweight(const PanelDims& pd, const double* Y, const double* V, const double* d, const double* rho,
                     const double* wmax, StageConsts sc, double* B, double* gram_part_out, cudaStream_t st) {
-  ProdArgs pa = base_args(pd);
-  pa.in0 = Y; pa.in1 = V; pa.d = d; pa.rho = rho; pa.wmax = wmax; pa.sc = sc; pa.Out = B; pa.gram_part = gram_part_out;
-  return launch_produce<OP_REWEIGHT>(pd, pa, st);
+  const int grid = std::min(nblk(pd.m * pd.q), kPanelBlocks * 8);
+  if (pd.cplx) k_reweight<true><<<grid, 256, 0, st>>>(Y, V, d, rho, wmax, sc, pd.m, pd.q, pd.pitch, B);
+  else k_reweight<false><<<grid, 256, 0, st>>>(Y, V, d, rho, wmax, sc, pd.m, pd.q, pd.pitch, B);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  if (gram_part_out) return launch_gram(pd, B, B, gram_part_out, st);
+  return SPEIGEN_OK;
 }
 
 int launch_extrapolate(const PanelDims& pd, const double* V, const double* V1, const double* V2, double a, double* Out,
                        double* gram_part_out, cudaStream_t st) {
-  ProdArgs pa = base_args(pd);
-  pa.in0 = V; pa.in1 = V1; pa.in2 = V2; pa.a = a; pa.Out = Out; pa.gram_part = gram_part_out;
-  return launch_produce<OP_EXTRAP>(pd, pa, st);
+  const int grid = std::min(nblk(pd.m * pd.ncr), kPanelBlocks * 8);
+  k_extrapolate<<<grid, 256, 0, st>>>(V, V1, V2, a, pd.m, pd.ncr, pd.pitch, Out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  if (gram_part_out) return launch_gram(pd, Out, Out, gram_part_out, st);
+  return SPEIGEN_OK;
 }
 
 int launch_absmin(const PanelDims& pd, const double* V, double* absmin_part, cudaStream_t st) {

@@ -166,7 +166,7 @@ int Solver::alloc_dev(Dev& d) {
   SPE_CUDA(cudaMalloc(&d.ws.partials, slots * slot_d * sizeof(double)));
   SPE_CUDA(cudaMalloc(&d.ws.counters, d.ws.n_counters * sizeof(int)));
   SPE_CUDA(cudaMemsetAsync(d.ws.counters, 0, d.ws.n_counters * sizeof(int), d.st));
-  const size_t glen = static_cast<size_t>(bq) * bq * e;
+  const size_t glen = static_cast<size_t>(bq * e) * (bq * e);   // real Gram / real hat form of the small matrix
   SPE_CUDA(cudaMalloc(&d.ps.gram_part, kPanelBlocks * glen * sizeof(double)));
   SPE_CUDA(cudaMalloc(&d.gram_part2, kPanelBlocks * glen * sizeof(double)));
   SPE_CUDA(cudaMalloc(&d.ps.col_part, kPanelBlocks * 2 * kMaxCols * sizeof(double)));
