@@ -203,8 +203,8 @@ int speigen_solver_mm_update(speigen_solver* s, const double* V_host, const doub
   API_TRY(S.set_qvecs(d, rho_vec));
   for (Dev& dv : S.devs) {
     cudaSetDevice(dv.ordinal);
-    API_TRY(launch_absmin(pd, dv.buf[BV], dv.absmin_a, dv.st));
-    API_TRY(launch_wmax(pd, dv.absmin_a, sc, dv.wmax, dv.st));
+    API_TRY(launch_absmin(pd, dv.buf[BV], dv.absmin_a, dv.ps.ticket, dv.st));
+    dv.wmax = const_cast<double*>(absmin_final(dv.absmin_a));
   }
   if (fused) {
     API_TRY(S.op_contract(BV, pd, NBUF, BB, BV, false, sc));
@@ -259,7 +259,7 @@ int speigen_solver_eig_small(speigen_solver* s, const double* C_host, int32_t nn
   Dev& d = S.devs[0];
   cudaSetDevice(d.ordinal);
   SPE_CUDA(cudaMemcpyAsync(d.ps.gram_part, rm.data(), rm.size() * sizeof(double), cudaMemcpyHostToDevice, d.st));
-  API_TRY(launch_small(pd, d.ps.gram_part, 1, SMALL_EIGVECS, d.Msmall, d.evals, d.status, d.st));
+  API_TRY(launch_small(pd, d.ps.gram_part, 1, SMALL_EIGVECS, d.Msmall, d.evals, d.status, nullptr, d.st));
   SPE_CUDA(cudaMemcpyAsync(wm.data(), d.Msmall, wm.size() * sizeof(double), cudaMemcpyDeviceToHost, d.st));
   SPE_CUDA(cudaMemcpyAsync(evals, d.evals, nn * sizeof(double), cudaMemcpyDeviceToHost, d.st));
   SPE_CUDA(cudaStreamSynchronize(d.st));

@@ -127,7 +127,8 @@ k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
     const bool ok = c < prm.epi.q;
     s_d[c] = (ok && prm.epi.d) ? prm.epi.d[c] : 1.0;
     s_rho[c] = (ok && prm.epi.rho) ? prm.epi.rho[c] : 0.0;
-    s_wmax[c] = (ok && prm.epi.wmax) ? prm.epi.wmax[c] : 0.0;
+    // epi.wmax carries min_j |V[j,c]|; the column max of the weights is w(min) (w is non-increasing)   R/spEigen.R:176
+    s_wmax[c] = (ok && prm.epi.wmax) ? weight_of_abs(prm.epi.wmax[c], prm.epi.sc) : 0.0;
   }
   __syncthreads();
 

@@ -26,7 +26,7 @@ struct EpiArgs {
   const double* V = nullptr;       // panel the weights / column dots are taken from (global rows)
   const double* d = nullptr;       // [q]
   const double* rho = nullptr;     // [q]
-  const double* wmax = nullptr;    // [q] column max of the weights (R/spEigen.R:176 apply(...,2,max))
+  const double* wmax = nullptr;    // [q] min_j |V[j,c]|: the kernel derives the column max of the weights w(min) (R/spEigen.R:176)
   double* dots = nullptr;          // per-row-tile partial column dots Re(conj(V) .* Y): [n_row_tiles][q]
   StageConsts sc{};
   int q = 0;

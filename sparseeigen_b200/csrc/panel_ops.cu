@@ -42,7 +42,9 @@ __device__ __forceinline__ double sum_parts_ilp(const double* p, int n, size_t s
 #pragma unroll
     for (int u = 0; u < 8; ++u) s[u] += __ldcg(p + static_cast<size_t>(k + u) * stride);
   }
-  for (int u = 0; k < n; ++k, ++u) s[u] += __ldcg(p + static_cast<size_t>(k) * stride);
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (k + u < n) s[u] += __ldcg(p + static_cast<size_t>(k + u) * stride);
   return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 __device__ __forceinline__ double min_parts_ilp(const double* p, int n, size_t stride) {
@@ -130,7 +132,8 @@ struct ApplyArgs {
   const double* Mh;
   double* Out;
   double* gram_part;
-  double* absmin_part;
+  double* absmin_part;   // [kPanelBlocks + 1][kMaxCols]; the last row receives the final column minima
+  int* ticket;
   int64_t m;
   int q, ncr, pitch, cplx;
 };
@@ -225,6 +228,8 @@ __global__ void __launch_bounds__(kPT) k_apply_mma(const ApplyArgs p) {
       for (int w = 1; w < kPT / 32; ++w) v = fmin(v, s_min[w][col]);
       p.absmin_part[static_cast<size_t>(blockIdx.x) * kMaxCols + threadIdx.x] = v;
     }
+    if (last_block_done(p.ticket) && threadIdx.x < p.q)
+      p.absmin_part[static_cast<size_t>(gridDim.x) * kMaxCols + threadIdx.x] = min_parts_ilp(p.absmin_part + threadIdx.x, gridDim.x, kMaxCols);
   }
   if (GRAM) {
     __syncthreads();
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(256) k_reweight(const double* Y, const double*
                                                   const double* wmax, StageConsts sc, int64_t m, int q, int pitch,
                                                   double* B) {
   __shared__ double s_d[kMaxCols], s_rho[kMaxCols], s_w[kMaxCols];
-  if (threadIdx.x < q) { s_d[threadIdx.x] = d[threadIdx.x]; s_rho[threadIdx.x] = rho[threadIdx.x]; s_w[threadIdx.x] = wmax[threadIdx.x]; }
+  if (threadIdx.x < q) { s_d[threadIdx.x] = d[threadIdx.x]; s_rho[threadIdx.x] = rho[threadIdx.x]; s_w[threadIdx.x] = weight_of_abs(wmax[threadIdx.x], sc); }   // `wmax` carries min|V| per column
   __syncthreads();
   const int64_t n = m * q;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n;
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(256) k_extrapolate(const double* V, const doub
 }
 
 template <bool CPLX>
-__global__ void __launch_bounds__(kPT) k_absmin(const double* V, int64_t m, int q, int pitch, double* absmin_part) {
+__global__ void __launch_bounds__(kPT) k_absmin(const double* V, int64_t m, int q, int pitch, double* absmin_part, int* ticket) {
   // thread layout: 8 row lanes x 32 column slots
   __shared__ double s_min[8][kMaxCols];
   int64_t r0, r1;
@@ -318,6 +323,8 @@ __global__ void __launch_bounds__(kPT) k_absmin(const double* V, int64_t m, int 
     for (int k = 1; k < 8; ++k) amin = fmin(amin, s_min[k][threadIdx.x]);
     absmin_part[static_cast<size_t>(blockIdx.x) * kMaxCols + threadIdx.x] = amin;
   }
+  if (last_block_done(ticket) && threadIdx.x < q)
+    absmin_part[static_cast<size_t>(gridDim.x) * kMaxCols + threadIdx.x] = min_parts_ilp(absmin_part + threadIdx.x, gridDim.x, kMaxCols);
 }
 
 __global__ void k_wmax(const double* absmin_part, int nparts, int q, StageConsts sc, double* wmax) {
@@ -368,10 +375,8 @@ __global__ void __launch_bounds__(kPT) k_squarem_norms(const double* V, const do
     col_part[blockIdx.x * 2 + 1] = tU;
   }
   if (last_block_done(ticket) && threadIdx.x == 0) {
-    double a = 0.0, b = 0.0;
-    for (unsigned k = 0; k < gridDim.x; ++k) { a += __ldcg(col_part + 2 * k); b += __ldcg(col_part + 2 * k + 1); }
-    norms[0] = sqrt(a);
-    norms[1] = sqrt(b);
+    norms[0] = sqrt(sum_parts_ilp(col_part, gridDim.x, 2));
+    norms[1] = sqrt(sum_parts_ilp(col_part + 1, gridDim.x, 2));
   }
 }
 
@@ -405,10 +410,8 @@ __global__ void __launch_bounds__(kPT) k_objective(const double* V0, int64_t m, 
     __shared__ double s_quad[kMaxCols], s_gs[kMaxCols];
     if (threadIdx.x < q) {
       const int cc = threadIdx.x;
-      double g = 0.0;
-      for (unsigned k = 0; k < gridDim.x; ++k) g += __ldcg(col_part + static_cast<size_t>(k) * kMaxCols + cc);
-      double qd = 0.0;
-      for (int k = 0; k < n_dot_parts; ++k) qd += __ldcg(dots_part + static_cast<size_t>(k) * q + cc);
+      const double g = sum_parts_ilp(col_part + cc, gridDim.x, kMaxCols);
+      const double qd = sum_parts_ilp(dots_part + cc, n_dot_parts, q);
       s_quad[cc] = qd;
       s_gs[cc] = g;
       out[1 + cc] = qd;
@@ -452,8 +455,7 @@ __global__ void __launch_bounds__(kPT) k_thres_norms(const double* V, int64_t m,
     col_part[static_cast<size_t>(blockIdx.x) * kMaxCols + threadIdx.x] = s;
   }
   if (last_block_done(ticket) && threadIdx.x < q) {
-    double s = 0.0;
-    for (unsigned k = 0; k < gridDim.x; ++k) s += __ldcg(col_part + static_cast<size_t>(k) * kMaxCols + threadIdx.x);
+    const double s = sum_parts_ilp(col_part + threadIdx.x, gridDim.x, kMaxCols);
     norms[threadIdx.x] = 1.0 / sqrt(s);   // nrm of R/spEigen.R:159
   }
 }
@@ -566,9 +568,7 @@ __global__ void __launch_bounds__(kPT) k_residual_norms(const double* ZW, const 
     col_part[static_cast<size_t>(blockIdx.x) * kMaxCols + threadIdx.x] = s;
   }
   if (last_block_done(ticket) && threadIdx.x < q) {
-    double s = 0.0;
-    for (unsigned k = 0; k < gridDim.x; ++k) s += __ldcg(col_part + static_cast<size_t>(k) * kMaxCols + threadIdx.x);
-    out[threadIdx.x] = sqrt(s);
+    out[threadIdx.x] = sqrt(sum_parts_ilp(col_part + threadIdx.x, gridDim.x, kMaxCols));
   }
 }
 
@@ -620,37 +620,79 @@ __device__ __forceinline__ void store_hat(double* Mh, int q, int a, int c, doubl
 
 template <bool CPLX>
 __global__ void __launch_bounds__(1024) k_small(const double* gram_part, int nparts, int q, int mode, double* Msmall,
-                                                double* evals, int* status) {
+                                                double* evals, int* status, double* warm) {
   extern __shared__ double sm[];
   constexpr int E = CPLX ? 2 : 1;
   double* F = sm;                      // column-major: F[(c*q + i)*E + e]
   double* W = F + q * q * E;
-  double* lam = W + q * q * E;         // [q]
+  double* T = W + q * q * E;           // scratch for the warm-start product
+  double* lam = T + q * q * E;         // [q]
   int* rank = reinterpret_cast<int*>(lam + q);
   __shared__ int s_rot;
   const int tid = threadIdx.x, nth = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
 
-  // fixed-order sum of the stage-1 real Gram partials R (ncr x ncr, ncr = q*E) and, for complex panels, the
-  // recombination C[a][b] = (R[2a][2b] + R[2a+1][2b+1]) + i (R[2a][2b+1] - R[2a+1][2b])
+  // fixed-order sum of the stage-1 real Gram partials R (ncr x ncr, ncr = q*E): every real entry is summed by H
+  // threads (partials k = h mod H, 8 independent chains each) and the H pieces are combined in order; then, for complex
+  // panels, C[a][b] = (R[2a][2b] + R[2a+1][2b+1]) + i (R[2a][2b+1] - R[2a+1][2b]).  scratch = W (free until the solve).
   {
     const int ncr = q * E;
-    const size_t pstride = static_cast<size_t>(ncr) * ncr;
-    for (int e = tid; e < q * q; e += nth) {
-      const int a = e / q, b = e - a * q;
-      double sr, si = 0.0;
-      if (CPLX) {
-        const double r00 = sum_parts_ilp(gram_part + static_cast<size_t>(2 * a) * ncr + 2 * b, nparts, pstride);
-        const double r11 = sum_parts_ilp(gram_part + static_cast<size_t>(2 * a + 1) * ncr + 2 * b + 1, nparts, pstride);
-        const double r01 = sum_parts_ilp(gram_part + static_cast<size_t>(2 * a) * ncr + 2 * b + 1, nparts, pstride);
-        const double r10 = sum_parts_ilp(gram_part + static_cast<size_t>(2 * a + 1) * ncr + 2 * b, nparts, pstride);
-        sr = r00 + r11;
-        si = r01 - r10;
-      } else {
-        sr = sum_parts_ilp(gram_part + static_cast<size_t>(a) * ncr + b, nparts, pstride);
+    const int nre = ncr * ncr;
+    int H = nth / nre;
+    if (H < 1) H = 1;
+    if (H > 4) H = 4;
+    const size_t pstride = static_cast<size_t>(nre);
+    double* R = W;                               // real Gram staging: nre doubles <= 2*q*q*E? (E=2: 4q^2 > 2q^2*... use F+W)
+    // F and W are contiguous (F first): together 2*q*q*E doubles >= nre for E=1 (2q^2 >= q^2) and E=2 (4q^2 >= 4q^2)
+    R = F;
+    __shared__ double s_piece[1024];
+    const int per = nth / H;                     // entries handled per pass
+    for (int base = 0; base < nre; base += per) {
+      const int loc = tid / H, h = tid - loc * H;
+      const int e = base + loc;
+      double v = 0.0;
+      if (loc < per && e < nre) {
+        // partials h, h+H, h+2H, ... in 8 chains
+        double sacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const double* gp = gram_part + e;
+        int k = h;
+        for (; k + 7 * H < nparts; k += 8 * H) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) sacc[u] += __ldcg(gp + static_cast<size_t>(k + u * H) * pstride);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (k + u * H < nparts) sacc[u] += __ldcg(gp + static_cast<size_t>(k + u * H) * pstride);
+        v = ((sacc[0] + sacc[1]) + (sacc[2] + sacc[3])) + ((sacc[4] + sacc[5]) + (sacc[6] + sacc[7]));
       }
-      F[(b * q + a) * E] = sr;
-      if (CPLX) F[(b * q + a) * E + 1] = si;
+      if (loc < per) s_piece[h * per + loc] = v;
+      __syncthreads();
+      if (tid < per && base + tid < nre) {
+        double t = s_piece[tid];
+        for (int hh = 1; hh < H; ++hh) t += s_piece[hh * per + tid];
+        R[base + tid] = t;                        // row-major real Gram R[x][y] at x*ncr + y
+      }
+      __syncthreads();
+    }
+    // R (in F..W storage) -> registers -> F (column-major, complex recombination), W = I
+    double cr[4], ci[4];
+    int cnt = 0;
+    for (int e = tid; e < q * q && cnt < 4; e += nth, ++cnt) {
+      const int a = e / q, b = e - a * q;
+      if (CPLX) {
+        cr[cnt] = R[(2 * a) * ncr + 2 * b] + R[(2 * a + 1) * ncr + 2 * b + 1];
+        ci[cnt] = R[(2 * a) * ncr + 2 * b + 1] - R[(2 * a + 1) * ncr + 2 * b];
+      } else {
+        cr[cnt] = R[a * ncr + b];
+        ci[cnt] = 0.0;
+      }
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int e = tid; e < q * q && cnt < 4; e += nth, ++cnt) {
+      const int a = e / q, b = e - a * q;
+      F[(b * q + a) * E] = cr[cnt];
+      if (CPLX) F[(b * q + a) * E + 1] = ci[cnt];
       W[(b * q + a) * E] = (a == b) ? 1.0 : 0.0;
       if (CPLX) W[(b * q + a) * E + 1] = 0.0;
     }
@@ -722,6 +764,37 @@ __global__ void __launch_bounds__(1024) k_small(const double* gram_part, int npa
     }
   }
 
+  // Warm start: consecutive calls from the same call site see slowly varying matrices, so start the one-sided
+  // Jacobi from the previous eigenvectors W0 (unitary): F = C W0, W = W0.  Every 16th call restarts from I so
+  // that rounding drift of W0's unitarity cannot accumulate.  warm = {q, count, W0 (column-major)}.
+  bool use_warm = false;
+  if (warm) {
+    use_warm = (warm[0] == static_cast<double>(q)) && (warm[1] < 16.0);
+    if (use_warm) {
+      for (int e = tid; e < q * q * E; e += nth) W[e] = warm[2 + e];
+      __syncthreads();
+      for (int e = tid; e < q * q; e += nth) {       // T[:,c] = C * W0[:,c]
+        const int a = e % q, c = e / q;
+        double sr = 0.0, si = 0.0;
+        for (int k = 0; k < q; ++k) {
+          const double cr = F[(k * q + a) * E], wr = W[(c * q + k) * E];
+          if (CPLX) {
+            const double ci2 = F[(k * q + a) * E + E - 1], wi = W[(c * q + k) * E + E - 1];
+            sr += cr * wr - ci2 * wi;
+            si += cr * wi + ci2 * wr;
+          } else {
+            sr += cr * wr;
+          }
+        }
+        T[(c * q + a) * E] = sr;
+        if (CPLX) T[(c * q + a) * E + E - 1] = si;
+      }
+      __syncthreads();
+      for (int e = tid; e < q * q * E; e += nth) F[e] = T[e];
+      __syncthreads();
+    }
+  }
+
   const int qe = q + (q & 1);
   const int npairs = qe / 2;
   const int n1 = qe - 1;
@@ -761,12 +834,15 @@ __global__ void __launch_bounds__(1024) k_small(const double* gram_part, int npa
           }
           al = warp_sum(al); be = warp_sum(be); gr = warp_sum(gr);
           if (CPLX) gi = warp_sum(gi);
-          const double g = CPLX ? hypot(gr, gi) : fabs(gr);
-          if (al > 0.0 && be > 0.0 && g > tol * sqrt(al) * sqrt(be)) {
-            const double er = gr / g, ei = CPLX ? gi / g : 0.0;
-            const double zeta = (be - al) / (2.0 * g);
-            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            const double cs = 1.0 / sqrt(1.0 + t * t);
+          const double g2 = CPLX ? (gr * gr + gi * gi) : gr * gr;
+          if (al > 0.0 && be > 0.0 && g2 > (tol * tol) * al * be) {
+            const double g = sqrt(g2);
+            const double ginv = 1.0 / g;
+            const double er = gr * ginv, ei = CPLX ? gi * ginv : 0.0;
+            // t = tan(theta): smaller root of t^2 + 2 zeta t - 1 = 0 with zeta = (be - al) / (2 g), written without zeta
+            const double dl = be - al;
+            const double t = (dl >= 0.0 ? 2.0 : -2.0) * g / (fabs(dl) + sqrt(dl * dl + 4.0 * g2));
+            const double cs = rsqrt(1.0 + t * t);
             const double sn = cs * t;
             // x' = cs*x - sn*conj(e)*y ; y' = sn*e*x + cs*y    (applied to F and W columns)
 #pragma unroll
@@ -810,6 +886,10 @@ __global__ void __launch_bounds__(1024) k_small(const double* gram_part, int npa
     if (!rot) break;
   }
 
+  if (warm) {
+    for (int e = tid; e < q * q * E; e += nth) warm[2 + e] = W[e];
+    if (tid == 0) { warm[1] = use_warm ? warm[1] + 1.0 : 0.0; warm[0] = static_cast<double>(q); }
+  }
   // eigenvalues as Rayleigh quotients lam_c = Re(w_c^H f_c)  (f_c = C w_c)
   for (int c = warp; c < q; c += (nth >> 5)) {
     double s = 0.0;
@@ -921,27 +1001,26 @@ int launch_gram(const PanelDims& pd, const double* A, const double* B, double* g
 }
 
 int launch_small(const PanelDims& pd, const double* gram_part, int nparts, int mode, double* Msmall, double* evals,
-                 int* status, cudaStream_t st) {
+                 int* status, double* warm, cudaStream_t st) {
   const int q = pd.q;
   const int qe = q + (q & 1);
-  int threads = 32 * (qe / 2);
-  if (threads < 64) threads = 64;
-  if (threads > 1024) threads = 1024;
-  const size_t smem = (2 * static_cast<size_t>(q) * q * (pd.cplx ? 2 : 1) + q) * sizeof(double) + q * sizeof(int) + 16;
+  (void)qe;
+  const int threads = 1024;   // the partial-sum prologue wants the parallelism; the Jacobi uses qe/2 warps of it
+  const size_t smem = (3 * static_cast<size_t>(q) * q * (pd.cplx ? 2 : 1) + q) * sizeof(double) + q * sizeof(int) + 16;
   if (pd.cplx) {
     static bool set_dev[64] = {};
     int dev_ = 0;
     cudaGetDevice(&dev_);
     bool& set = set_dev[dev_ & 63];
-    if (!set) { SPE_CUDA(cudaFuncSetAttribute(k_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
-    k_small<true><<<1, threads, smem, st>>>(gram_part, nparts, q, mode, Msmall, evals, status);
+    if (!set) { SPE_CUDA(cudaFuncSetAttribute(k_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024)); set = true; }
+    k_small<true><<<1, threads, smem, st>>>(gram_part, nparts, q, mode, Msmall, evals, status, warm);
   } else {
     static bool set_dev[64] = {};
     int dev_ = 0;
     cudaGetDevice(&dev_);
     bool& set = set_dev[dev_ & 63];
-    if (!set) { SPE_CUDA(cudaFuncSetAttribute(k_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
-    k_small<false><<<1, threads, smem, st>>>(gram_part, nparts, q, mode, Msmall, evals, status);
+    if (!set) { SPE_CUDA(cudaFuncSetAttribute(k_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024)); set = true; }
+    k_small<false><<<1, threads, smem, st>>>(gram_part, nparts, q, mode, Msmall, evals, status, warm);
   }
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
@@ -971,9 +1050,9 @@ static int launch_apply_nt(const ApplyArgs& pa, bool gram, cudaStream_t st) {
 }
 
 int launch_apply(const PanelDims& pd, const double* A, const double* Msmall, double* Out, double* gram_part_out,
-                 double* absmin_part_out, cudaStream_t st) {
+                 double* absmin_part_out, int* ticket, cudaStream_t st) {
   ApplyArgs pa{};
-  pa.A = A; pa.Mh = Msmall; pa.Out = Out; pa.absmin_part = absmin_part_out;
+  pa.A = A; pa.Mh = Msmall; pa.Out = Out; pa.absmin_part = absmin_part_out; pa.ticket = ticket;
   pa.m = pd.m; pa.q = pd.q; pa.ncr = pd.ncr; pa.pitch = pd.pitch; pa.cplx = pd.cplx;
   const int nt = (pd.ncr + 7) / 8;
   const bool fuse = gram_part_out != nullptr && nt <= 5;   // Gram accumulators fit in registers
@@ -1015,9 +1094,9 @@ int launch_extrapolate(const PanelDims& pd, const double* V, const double* V1, c
   return SPEIGEN_OK;
 }
 
-int launch_absmin(const PanelDims& pd, const double* V, double* absmin_part, cudaStream_t st) {
-  if (pd.cplx) k_absmin<true><<<kPanelBlocks, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, absmin_part);
-  else k_absmin<false><<<kPanelBlocks, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, absmin_part);
+int launch_absmin(const PanelDims& pd, const double* V, double* absmin_part, int* ticket, cudaStream_t st) {
+  if (pd.cplx) k_absmin<true><<<kPanelBlocks, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, absmin_part, ticket);
+  else k_absmin<false><<<kPanelBlocks, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, absmin_part, ticket);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

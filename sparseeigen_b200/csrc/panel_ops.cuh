@@ -38,19 +38,22 @@ struct PanelScratch {
 };
 
 int launch_gram(const PanelDims& pd, const double* A, const double* B, double* gram_part, cudaStream_t st);
+// warm (nullable): {q, count, W0[q*q*(1+cplx)]} per call site - Jacobi warm start from the previous eigenvectors
 int launch_small(const PanelDims& pd, const double* gram_part, int nparts, int mode, double* Msmall, double* evals,
-                 int* status, cudaStream_t st);
+                 int* status, double* warm, cudaStream_t st);
 // Out = A * Msmall ; optional fused stage-1 reductions of Out: Gram partials and column min|.| partials.
 int launch_apply(const PanelDims& pd, const double* A, const double* Msmall, double* Out, double* gram_part_out,
-                 double* absmin_part_out, cudaStream_t st);
-// B = d*Y - (w(|V|) - wmax) * V * rho  (+ Gram partials of B)
+                 double* absmin_part_out, int* ticket, cudaStream_t st);
+// B = d*Y - (w(|V|) - w(amin)) * V * rho  (+ Gram partials of B); `wmax` carries the column minima of |V|
 int launch_reweight(const PanelDims& pd, const double* Y, const double* V, const double* d, const double* rho,
                     const double* wmax, StageConsts sc, double* B, double* gram_part_out, cudaStream_t st);
 // Out = V - 2 a R + a^2 U,  R = V1 - V, U = V2 - V1 - R   (+ Gram partials of Out)   R/spEigen.R:121-127
 int launch_extrapolate(const PanelDims& pd, const double* V, const double* V1, const double* V2, double a, double* Out,
                        double* gram_part_out, cudaStream_t st);
 // column min|.| partials of a panel, and wmax[c] = w(min_j |V[j,c]|) from them (R/spEigen.R:176 `apply(w,2,max)`).
-int launch_absmin(const PanelDims& pd, const double* V, double* absmin_part, cudaStream_t st);
+// absmin_part: [kPanelBlocks + 1][kMaxCols]; the last row receives the final column minima (last-block reduction)
+int launch_absmin(const PanelDims& pd, const double* V, double* absmin_part, int* ticket, cudaStream_t st);
+inline const double* absmin_final(const double* absmin_part) { return absmin_part + static_cast<size_t>(kPanelBlocks) * kMaxCols; }
 int launch_wmax(const PanelDims& pd, const double* absmin_part, StageConsts sc, double* wmax, cudaStream_t st);
 // norms[0..1] = {||V1 - V||_F, ||V2 - 2 V1 + V||_F}
 int launch_squarem_norms(const PanelDims& pd, const double* V, const double* V1, const double* V2,

@@ -172,15 +172,16 @@ int Solver::alloc_dev(Dev& d) {
   SPE_CUDA(cudaMalloc(&d.ps.col_part, kPanelBlocks * 2 * kMaxCols * sizeof(double)));
   SPE_CUDA(cudaMalloc(&d.ps.ticket, sizeof(int)));
   SPE_CUDA(cudaMemsetAsync(d.ps.ticket, 0, sizeof(int), d.st));
-  SPE_CUDA(cudaMalloc(&d.absmin_a, kPanelBlocks * kMaxCols * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.absmin_b, kPanelBlocks * kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.absmin_a, (kPanelBlocks + 1) * kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.absmin_b, (kPanelBlocks + 1) * kMaxCols * sizeof(double)));
   SPE_CUDA(cudaMalloc(&d.Msmall, glen * sizeof(double)));
   SPE_CUDA(cudaMalloc(&d.evals, kMaxCols * sizeof(double)));
+  SPE_CUDA(cudaMalloc(&d.warm, 4 * kWarmStride * sizeof(double)));
+  SPE_CUDA(cudaMemsetAsync(d.warm, 0, 4 * kWarmStride * sizeof(double), d.st));
   SPE_CUDA(cudaMalloc(&d.status, sizeof(int)));
   SPE_CUDA(cudaMemsetAsync(d.status, 0, sizeof(int), d.st));
   SPE_CUDA(cudaMalloc(&d.dvec, kMaxCols * sizeof(double)));
   SPE_CUDA(cudaMalloc(&d.rho, kMaxCols * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.wmax, kMaxCols * sizeof(double)));
   const size_t ntiles = static_cast<size_t>((d.a_rows + kTJ - 1) / kTJ) + 1;
   SPE_CUDA(cudaMalloc(&d.dots_part, std::max<size_t>(ntiles, kPanelBlocks) * kMaxCols * sizeof(double)));
   SPE_CUDA(cudaMalloc(&d.dots_gather, static_cast<size_t>(prob.world) * kMaxCols * sizeof(double)));
@@ -200,8 +201,8 @@ void Solver::destroy() {
     if (d.st) cudaStreamSynchronize(d.st);
     if (d.comm && nccl_api()) nccl_api()->CommDestroy(d.comm);
     void* ptrs[] = {d.A, d.hat, d.Tdata, d.gather, d.ws.partials, d.ws.counters, d.ps.gram_part, d.gram_part2,
-                    d.ps.col_part, d.ps.ticket, d.absmin_a, d.absmin_b, d.Msmall, d.evals, d.status, d.dvec, d.rho,
-                    d.wmax, d.dots_part, d.dots_gather, d.scal, d.vecm, d.vecm2, d.scan_part, d.out_cm, d.flush};
+                    d.ps.col_part, d.ps.ticket, d.absmin_a, d.absmin_b, d.Msmall, d.evals, d.warm, d.status, d.dvec, d.rho,
+                    d.dots_part, d.dots_gather, d.scal, d.vecm, d.vecm2, d.scan_part, d.out_cm, d.flush};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     for (int b = 0; b < NBUF; ++b)
@@ -505,15 +506,16 @@ int Solver::op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vep
 }
 
 // ---- polar factor (K3 + applies):  out = in (in^H in)^{-1/2}, two Gram passes ------
-int Solver::op_polar(Buf in, Buf out, const PanelDims& pd, bool have_gram, double* /*unused*/, int which_absmin) {
+int Solver::op_polar(Buf in, Buf out, const PanelDims& pd, bool have_gram, double* /*unused*/, int which_absmin, int warm_slot) {
   for (Dev& d : devs) {
     SPE_CUDA(cudaSetDevice(d.ordinal));
     if (!have_gram) SPE_TRY(launch_gram(pd, d.buf[in], d.buf[in], d.ps.gram_part, d.st));
-    SPE_TRY(launch_small(pd, d.ps.gram_part, kPanelBlocks, SMALL_INVSQRT, d.Msmall, d.evals, d.status, d.st));
-    SPE_TRY(launch_apply(pd, d.buf[in], d.Msmall, d.buf[BT2], d.gram_part2, nullptr, d.st));
-    SPE_TRY(launch_small(pd, d.gram_part2, kPanelBlocks, SMALL_INVSQRT, d.Msmall, d.evals, d.status, d.st));
+    double* warm = (warm_slot >= 0) ? d.warm + static_cast<size_t>(warm_slot) * kWarmStride : nullptr;
+    SPE_TRY(launch_small(pd, d.ps.gram_part, kPanelBlocks, SMALL_INVSQRT, d.Msmall, d.evals, d.status, warm, d.st));
+    SPE_TRY(launch_apply(pd, d.buf[in], d.Msmall, d.buf[BT2], d.gram_part2, nullptr, d.ps.ticket, d.st));
+    SPE_TRY(launch_small(pd, d.gram_part2, kPanelBlocks, SMALL_INVSQRT, d.Msmall, d.evals, d.status, nullptr, d.st));
     double* am = which_absmin == 1 ? d.absmin_a : (which_absmin == 2 ? d.absmin_b : nullptr);
-    SPE_TRY(launch_apply(pd, d.buf[BT2], d.Msmall, d.buf[out], nullptr, am, d.st));
+    SPE_TRY(launch_apply(pd, d.buf[BT2], d.Msmall, d.buf[out], nullptr, am, d.ps.ticket, d.st));
   }
   return SPEIGEN_OK;
 }
@@ -522,6 +524,10 @@ int Solver::op_polar(Buf in, Buf out, const PanelDims& pd, bool have_gram, doubl
 int Solver::init_vectors(const double* V0_host, speigen_out* out) {
   if (!prepared) SPE_TRY(prepare());
   const double t0 = now_s();
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_CUDA(cudaMemsetAsync(d.warm, 0, 4 * kWarmStride * sizeof(double), d.st));
+  }
   const StageConsts sc0 = make_stage(0.1, 0.1);
   int passes = 0;
   bool converged = false;
@@ -547,9 +553,9 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
       for (Dev& d : devs) {
         SPE_CUDA(cudaSetDevice(d.ordinal));
         SPE_TRY(launch_gram(pdb, d.buf[BQ], d.buf[BZ], d.ps.gram_part, d.st));
-        SPE_TRY(launch_small(pdb, d.ps.gram_part, kPanelBlocks, SMALL_EIGVECS, d.Msmall, d.evals, d.status, d.st));
-        SPE_TRY(launch_apply(pdb, d.buf[BQ], d.Msmall, d.buf[BV1], nullptr, nullptr, d.st));   // Ritz vectors
-        SPE_TRY(launch_apply(pdb, d.buf[BZ], d.Msmall, d.buf[BV2], nullptr, nullptr, d.st));   // S * Ritz vectors
+        SPE_TRY(launch_small(pdb, d.ps.gram_part, kPanelBlocks, SMALL_EIGVECS, d.Msmall, d.evals, d.status, nullptr, d.st));
+        SPE_TRY(launch_apply(pdb, d.buf[BQ], d.Msmall, d.buf[BV1], nullptr, nullptr, d.ps.ticket, d.st));   // Ritz vectors
+        SPE_TRY(launch_apply(pdb, d.buf[BZ], d.Msmall, d.buf[BV2], nullptr, nullptr, d.ps.ticket, d.st));   // S * Ritz vectors
         SPE_TRY(launch_residual_norms(pdb, d.buf[BV2], d.buf[BV1], d.evals, d.ps, d.scal + 64, d.st));
         SPE_CUDA(cudaMemcpyAsync(d.scal, d.evals, bq * sizeof(double), cudaMemcpyDeviceToDevice, d.st));
       }
@@ -566,7 +572,7 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
       if (resid_rel > 0.5 * prev) ++stall; else stall = 0;
       if (stall >= 3 && resid_rel <= 1e-11) { converged = true; break; }
       prev = std::min(prev, resid_rel);
-      SPE_TRY(op_polar(BV2, BQ, pdb, false, nullptr, 0));
+      SPE_TRY(op_polar(BV2, BQ, pdb, false, nullptr, 0, WARM_INIT));
       {
         Dev& d = devs[0];
         int st = 0;
@@ -623,6 +629,10 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
 int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) {
   if (!inited) { set_error("solver_run before solver_init"); return SPEIGEN_ERR_ARG; }
   const double t0 = now_s();
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_CUDA(cudaMemsetAsync(d.warm, 0, 4 * kWarmStride * sizeof(double), d.st));
+  }
   std::vector<double> dv(q), rv(q);
   if (d_in) for (int c = 0; c < q; ++c) dv[c] = d_in[c];
   else speigen_default_d(q, dv.data());
@@ -641,7 +651,7 @@ int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) 
   SPE_TRY(op_contract(BV, pdq, BY, NBUF, NBUF, false, sc));
   for (Dev& d : devs) {
     SPE_CUDA(cudaSetDevice(d.ordinal));
-    SPE_TRY(launch_absmin(pdq, d.buf[BV], d.absmin_a, d.st));
+    SPE_TRY(launch_absmin(pdq, d.buf[BV], d.absmin_a, d.ps.ticket, d.st));
   }
   Buf bV = BV, bV0 = BV0, bY = BY, bY0 = BY0;
   bool absmin_swapped = false;   // false: accepted iterate's partials live in absmin_a
@@ -656,26 +666,26 @@ int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) 
       // ---- V1 = MMupdate(V) ----
       for (Dev& d : devs) {
         SPE_CUDA(cudaSetDevice(d.ordinal));
-        SPE_TRY(launch_wmax(pdq, absmin_swapped ? d.absmin_b : d.absmin_a, sc, d.wmax, d.st));
+        d.wmax = const_cast<double*>(absmin_final(absmin_swapped ? d.absmin_b : d.absmin_a));   // min|V| -> weights' column max
         SPE_TRY(launch_reweight(pdq, d.buf[bY], d.buf[bV], d.dvec, d.rho, d.wmax, sc, d.buf[BB], d.ps.gram_part, d.st));
       }
       const int other = absmin_swapped ? 1 : 2;   // scratch min|.| partial buffer (1 = a, 2 = b)
-      SPE_TRY(op_polar(BB, BV1, pdq, true, nullptr, other));
+      SPE_TRY(op_polar(BB, BV1, pdq, true, nullptr, other, WARM_MM));
       // ---- V2 = MMupdate(V1): contraction with the reweighting fused into its epilogue ----
       for (Dev& d : devs) {
         SPE_CUDA(cudaSetDevice(d.ordinal));
-        SPE_TRY(launch_wmax(pdq, other == 1 ? d.absmin_a : d.absmin_b, sc, d.wmax, d.st));
+        d.wmax = const_cast<double*>(absmin_final(other == 1 ? d.absmin_a : d.absmin_b));
       }
       if (fused) {
         SPE_TRY(op_contract(BV1, pdq, NBUF, BB, BV1, false, sc));
-        SPE_TRY(op_polar(BB, BV2, pdq, false, nullptr, 0));
+        SPE_TRY(op_polar(BB, BV2, pdq, false, nullptr, 0, WARM_MM));
       } else {
         SPE_TRY(op_contract(BV1, pdq, BT1, NBUF, NBUF, false, sc));
         for (Dev& d : devs) {
           SPE_CUDA(cudaSetDevice(d.ordinal));
           SPE_TRY(launch_reweight(pdq, d.buf[BT1], d.buf[BV1], d.dvec, d.rho, d.wmax, sc, d.buf[BB], d.ps.gram_part, d.st));
         }
-        SPE_TRY(op_polar(BB, BV2, pdq, true, nullptr, 0));
+        SPE_TRY(op_polar(BB, BV2, pdq, true, nullptr, 0, WARM_MM));
       }
       // ---- SQUAREM step length  (R/spEigen.R:121-123) ----
       for (Dev& d : devs) {
@@ -693,7 +703,7 @@ int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) 
           SPE_CUDA(cudaSetDevice(d.ordinal));
           SPE_TRY(launch_extrapolate(pdq, d.buf[bV], d.buf[BV1], d.buf[BV2], a, d.buf[BT1], d.ps.gram_part, d.st));
         }
-        SPE_TRY(op_polar(BT1, bV0, pdq, true, nullptr, other));
+        SPE_TRY(op_polar(BT1, bV0, pdq, true, nullptr, other, WARM_EXTRAP));
         SPE_TRY(op_contract(bV0, pdq, bY0, NBUF, bV0, true, sc));
         for (Dev& d : devs) {
           SPE_CUDA(cudaSetDevice(d.ordinal));
@@ -810,7 +820,7 @@ int Solver::mm_steps(int nsteps, int stage, double rho, const double* d_in, floa
   const StageConsts sc = make_stage(pp[stage], ee[stage]);
   for (Dev& d : devs) {
     SPE_CUDA(cudaSetDevice(d.ordinal));
-    SPE_TRY(launch_absmin(pdq, d.buf[BV], d.absmin_a, d.st));
+    SPE_TRY(launch_absmin(pdq, d.buf[BV], d.absmin_a, d.ps.ticket, d.st));
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ms_out) {
@@ -823,10 +833,10 @@ int Solver::mm_steps(int nsteps, int stage, double rho, const double* d_in, floa
   for (int i = 0; i < nsteps; ++i) {
     for (Dev& d : devs) {
       SPE_CUDA(cudaSetDevice(d.ordinal));
-      SPE_TRY(launch_wmax(pdq, d.absmin_a, sc, d.wmax, d.st));
+      d.wmax = const_cast<double*>(absmin_final(d.absmin_a));
     }
     SPE_TRY(op_contract(BV, pdq, NBUF, BB, BV, false, sc));     // K1 with the fused reweighting epilogue
-    SPE_TRY(op_polar(BB, BV1, pdq, false, nullptr, 1));         // K3 (+ min|V| partials for the next weights)
+    SPE_TRY(op_polar(BB, BV1, pdq, false, nullptr, 1, WARM_MM)); // K3 (+ min|V| partials for the next weights)
     for (Dev& d : devs) std::swap(d.buf[BV], d.buf[BV1]);
   }
   if (ms_out) {

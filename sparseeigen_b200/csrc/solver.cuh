@@ -13,6 +13,8 @@
 
 namespace speigen {
 
+constexpr size_t kWarmStride = 2 + 2 * kMaxCols * kMaxCols;
+enum WarmSlot { WARM_MM = 0, WARM_EXTRAP = 1, WARM_INIT = 2 };
 enum Buf { BV = 0, BV1, BV2, BV0, BY, BY0, BB, BT1, BT2, BVX, BQ, BZ, NBUF };
 
 struct Dev {
@@ -38,10 +40,11 @@ struct Dev {
   double* absmin_b = nullptr;  // min|.| partials of V1 / V0 candidates
   double* Msmall = nullptr;
   double* evals = nullptr;
+  double* warm = nullptr;      // Jacobi warm-start slots (kWarmStride doubles each)
   int* status = nullptr;
   double* dvec = nullptr;
   double* rho = nullptr;
-  double* wmax = nullptr;
+  double* wmax = nullptr;      // non-owning: final column minima of |V| (last row of absmin_a / absmin_b)
   double* dots_part = nullptr;
   double* dots_gather = nullptr;
   double* scal = nullptr;      // device scalars [256]
@@ -87,7 +90,7 @@ class Solver {
 
   // building blocks (all devices)
   int op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vepi, bool want_dots, const StageConsts& sc);
-  int op_polar(Buf in, Buf out, const PanelDims& pd, bool have_gram, double* absmin_of_out_sel /*0,1*/, int which);
+  int op_polar(Buf in, Buf out, const PanelDims& pd, bool have_gram, double* unused, int which_absmin, int warm_slot = -1);
   int op_upload_panel(const double* host_cm, Buf b, const PanelDims& pd);
   int op_download_panel(Buf b, const PanelDims& pd, double* host_cm);
   int sync_all();
