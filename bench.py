@@ -211,6 +211,7 @@ def main():
         solver.init_comm(bytes(idt.cpu().numpy().tobytes()))
     else:
         solver.init_comm(None)
+    torch.cuda.synchronize()                  # S was produced on torch's stream; the library copies on its own
     solver.load_device(S.data_ptr(), m)
     S_host = None
     want_host = (rank == 0 and world == 1 and (not args.no_e2e or not args.no_cpu))

@@ -59,6 +59,8 @@ typedef struct speigen_cfg {
   int32_t first_device;      /* single-process mode: first CUDA ordinal */
   int32_t fused_epilogue;    /* 1: reweighting fused into the contraction epilogue where the data flow allows */
   int32_t verbose;
+  int32_t pd_check_passes;   /* 4: block power passes on (theta_1 I - S) whose smallest Ritz value of S is tested against pd_tol
+                                (R/spEigen.R:77 tests the full spectrum; a Ritz value < pd_tol proves S is not PD) */
 } speigen_cfg;
 
 void speigen_cfg_default(speigen_cfg* cfg);
@@ -161,6 +163,9 @@ int speigen_solver_time_contract(speigen_solver* s, int32_t ncols, int32_t reps,
 /* Device-to-device load of shard `local_idx` from a caller buffer already in HBM (same row meaning as
  * speigen_solver_shard_buffer; src_ld = source row pitch in doubles). */
 int speigen_solver_load_device(speigen_solver* s, int32_t local_idx, const double* dev_src, int64_t src_ld);
+/* Same, for rows [row0, row0 + nrows) of the shard only (lets a caller stream a matrix larger than its staging buffer). */
+int speigen_solver_load_device_rows(speigen_solver* s, int32_t local_idx, int64_t row0, int64_t nrows,
+                                    const double* dev_src, int64_t src_ld);
 /* `nsteps` back-to-back MM updates V <- spEigenMMupdate(V) (R/spEigen.R:167-183) on the resident iterate at
  * continuation stage `stage` (0-based).  ms_out == NULL: asynchronous.  ms_out != NULL: the nsteps are bracketed by
  * CUDA events on the launching stream (synchronised on both sides) and the elapsed device time is returned. */

@@ -41,7 +41,7 @@ class Cfg(C.Structure):
         ("tol_factor", C.c_double), ("backtrack_slack", C.c_double), ("rank_tol", C.c_double), ("pd_tol", C.c_double),
         ("max_backtracks", C.c_int32), ("init_max_passes", C.c_int32), ("init_tol", C.c_double),
         ("init_block", C.c_int32), ("init_seed", C.c_uint64), ("check_symmetric", C.c_int32), ("check_na", C.c_int32),
-        ("n_gpus", C.c_int32), ("first_device", C.c_int32), ("fused_epilogue", C.c_int32), ("verbose", C.c_int32),
+        ("n_gpus", C.c_int32), ("first_device", C.c_int32), ("fused_epilogue", C.c_int32), ("verbose", C.c_int32), ("pd_check_passes", C.c_int32),
     ]
 
 
@@ -108,6 +108,7 @@ def lib():
     L.speigen_solver_launch_count.restype = C.c_int64
     L.speigen_solver_stream.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
     L.speigen_solver_load_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+    L.speigen_solver_load_device_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]
     L.speigen_solver_mm_steps.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, _dp, C.POINTER(C.c_float)]
     L.speigen_solver_sync.argtypes = [C.c_void_p]
     L.speigen_solver_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
@@ -374,6 +375,9 @@ class Solver:
 
     def load_device(self, dev_ptr: int, src_ld: int, local_idx=0):
         _check(self.L.speigen_solver_load_device(self.h, local_idx, C.c_void_p(dev_ptr), src_ld))
+
+    def load_device_rows(self, row0: int, nrows: int, dev_ptr: int, src_ld: int, local_idx=0):
+        _check(self.L.speigen_solver_load_device_rows(self.h, local_idx, row0, nrows, C.c_void_p(dev_ptr), src_ld))
 
     def mm_steps(self, nsteps, stage=0, rho=0.5, d=None, timed=False):
         """nsteps MM updates on the resident iterate; timed=True returns the CUDA-event elapsed ms."""

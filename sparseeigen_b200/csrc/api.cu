@@ -45,6 +45,7 @@ void speigen_cfg_default(speigen_cfg* c) {
   c->first_device = 0;
   c->fused_epilogue = 1;
   c->verbose = 0;
+  c->pd_check_passes = 4;
 }
 
 const char* speigen_last_error(void) { return last_error(); }
@@ -284,6 +285,9 @@ int speigen_solver_time_contract(speigen_solver* s, int32_t ncols, int32_t reps,
 
 int speigen_solver_load_device(speigen_solver* s, int32_t li, const double* dev_src, int64_t src_ld) {
   return s->impl.load_device(li, dev_src, src_ld);
+}
+int speigen_solver_load_device_rows(speigen_solver* s, int32_t li, int64_t row0, int64_t nrows, const double* dev_src, int64_t src_ld) {
+  return s->impl.load_device_rows(li, row0, nrows, dev_src, src_ld);
 }
 int speigen_solver_mm_steps(speigen_solver* s, int32_t nsteps, int32_t stage, double rho, const double* d, float* ms_out) {
   return s->impl.mm_steps(nsteps, stage, rho, d, ms_out);

@@ -572,6 +572,15 @@ __global__ void __launch_bounds__(kPT) k_residual_norms(const double* ZW, const 
   }
 }
 
+// Out = alpha * X + beta * Y on the valid m x ncr region
+__global__ void k_axpby(const double* X, const double* Y, double alpha, double beta, int64_t m, int ncr, int pitch, double* Out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= m * ncr) return;
+  const int64_t r = idx / ncr;
+  const size_t g = static_cast<size_t>(r) * pitch + (idx - r * ncr);
+  Out[g] = alpha * X[g] + beta * Y[g];
+}
+
 __global__ void k_take_columns(const double* In, int64_t m, int ncr_out, int pitch_in, int pitch_out, double* Out) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= m * ncr_out) return;
@@ -1178,6 +1187,12 @@ int launch_residual_norms(const PanelDims& pd, const double* ZW, const double* Q
                           const PanelScratch& sc, double* out, cudaStream_t st) {
   if (pd.cplx) k_residual_norms<true><<<kPanelBlocks, kPT, 0, st>>>(ZW, QW, evals, pd.m, pd.q, pd.pitch, sc.col_part, sc.ticket, out);
   else k_residual_norms<false><<<kPanelBlocks, kPT, 0, st>>>(ZW, QW, evals, pd.m, pd.q, pd.pitch, sc.col_part, sc.ticket, out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_axpby(const PanelDims& pd, const double* X, const double* Y, double alpha, double beta, double* Out, cudaStream_t st) {
+  k_axpby<<<nblk(pd.m * pd.ncr), 256, 0, st>>>(X, Y, alpha, beta, pd.m, pd.ncr, pd.pitch, Out);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

@@ -100,6 +100,7 @@ class Solver {
   // bench: `nsteps` back-to-back MM updates V <- spEigenMMupdate(V) (R/spEigen.R:167-183) at continuation stage `stage`
   int mm_steps(int nsteps, int stage, double rho, const double* d, float* ms_out);
   int load_device(int local_idx, const double* dev_src, int64_t src_ld);
+  int load_device_rows(int local_idx, int64_t row0, int64_t nrows, const double* dev_src, int64_t src_ld);
   // per-launch device timing of the contraction kernel (CUDA events on the launching stream of device 0)
   void enable_kernel_timing(bool on);
   int kernel_time(double* ms_total, int* launches);

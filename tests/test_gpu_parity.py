@@ -255,6 +255,21 @@ def test_reference_testthat_behaviours():
     with pytest.raises(sb.SpEigenError, match="rank"): sb.spEigen(X[:3], 5, data=True)  # :69
 
 
+def test_not_pd_detected_beyond_the_top_block():
+    """R/spEigen.R:77: a negative eigenvalue far below the leading block is found by the shifted power probe."""
+    rng = np.random.default_rng(17)
+    m = 400
+    A = rng.standard_normal((m, 60))
+    v = rng.standard_normal(m); v /= np.linalg.norm(v)
+    S = A @ A.T / 60 - 2.0 * np.outer(v, v)
+    S = (S + S.T) / 2
+    assert np.linalg.eigvalsh(S)[0] < -1.0
+    with pytest.raises(sb.SpEigenError, match="not PD"): sb.spEigen(S, 3)
+    with pytest.raises(o.SpEigenError, match="not PD"): o.spEigen(S, 3)
+    r = sb.spEigen(A @ A.T / 60, 3)                       # the PSD part alone passes (rank-deficient, lambda_min = 0)
+    assert r["vectors"].shape == (m, 3)
+
+
 # ---------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE config 4: m = 50000, q = 20) — no oracle at this size
 # ---------------------------------------------------------------------------------------------------
@@ -265,6 +280,7 @@ def test_full_size_properties():
     S = symmetrize_(synth_cov_rows(m, n, q, 0.02, 0, m, torch.device("cuda", 0)))
     with sb.Solver(m, q) as s:
         s.init_comm(None)
+        torch.cuda.synchronize()
         s.load_device(S.data_ptr(), m)
         rng = np.random.default_rng(0)
         U, W = rng.standard_normal((m, q)), rng.standard_normal((m, q))

@@ -6,7 +6,7 @@ import sparseeigen_b200 as sb
 m = 50000
 S = torch.randn(m, m, dtype=torch.float64, device="cuda")
 s = sb.Solver(m, 32, check_symmetric=0, check_na=0, init_block=32)
-s.init_comm(None); s.load_device(S.data_ptr(), m); del S; torch.cuda.empty_cache()
+s.init_comm(None); torch.cuda.synchronize(); s.load_device(S.data_ptr(), m); del S; torch.cuda.empty_cache()
 ncols = int(os.environ.get("NCOLS", 20)); reps = int(os.environ.get("REPS", 150))
 res = {"hybrid": [], "dmma": []}
 s.time_contract(ncols, 100, flush_l2=False)   # heat up

@@ -6,7 +6,7 @@ import sparseeigen_b200 as sb
 m = 50000
 S = torch.randn(m, m, dtype=torch.float64, device="cuda")
 s = sb.Solver(m, 32, check_symmetric=0, check_na=0, init_block=32)
-s.init_comm(None); s.load_device(S.data_ptr(), m); del S; torch.cuda.empty_cache()
+s.init_comm(None); torch.cuda.synchronize(); s.load_device(S.data_ptr(), m); del S; torch.cuda.empty_cache()
 def sample(tag, fn):
     p = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_thermal_slowdown",
                           "--format=csv,noheader,nounits", "-lms", "20", "-i", "0"], stdout=subprocess.PIPE, text=True)
