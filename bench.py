@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-store exchange or NCCL allgather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -202,7 +203,7 @@ def main():
     if world == 1:
         symmetrize_(S)
     solver = sb.Solver(m, q, world=world, rank=rank, local_gpus=1, first_device=local_rank,
-                       check_symmetric=1 if world == 1 else 0)
+                       check_symmetric=1 if world == 1 else 0, p2p_exchange=1 if args.exchange == "p2p" else 0)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -269,7 +270,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload, "sharding": f"S row-sharded over {world} GPU(s), NCCL allgather per contraction",
+            "config": {"workload": workload, "sharding": f"S row-sharded over {world} GPU(s), exchange per contraction: {solver.exchange_mode()}",
                        "l2": "inputs larger than L2 (S shard = %.1f GB per GPU streamed every step)" % (8.0 * rows_local * m / 1e9),
                        "step": "one MM update = fused contraction+reweight, 2x(Gram, Jacobi, apply)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -61,6 +61,8 @@ typedef struct speigen_cfg {
   int32_t verbose;
   int32_t pd_check_passes;   /* 4: block power passes on (theta_1 I - S) whose smallest Ritz value of S is tested against pd_tol
                                 (R/spEigen.R:77 tests the full spectrum; a Ritz value < pd_tol proves S is not PD) */
+  int32_t p2p_exchange;      /* 1: row-sharded covariance exchanges its m x q row blocks with peer-memory stores fused into the
+                                contraction epilogue (NVLink P2P / CUDA IPC); 0: NCCL allgather after the kernel */
 } speigen_cfg;
 
 void speigen_cfg_default(speigen_cfg* cfg);
@@ -172,6 +174,8 @@ int speigen_solver_load_device_rows(speigen_solver* s, int32_t local_idx, int64_
 int speigen_solver_mm_steps(speigen_solver* s, int32_t nsteps, int32_t stage, double rho, const double* d_or_null,
                             float* ms_out);
 int speigen_solver_sync(speigen_solver* s);
+/* 0: single GPU (no exchange), 1: NCCL collectives, 2: fused peer-store exchange (valid after speigen_solver_init_comm) */
+int speigen_solver_exchange_mode(speigen_solver* s);
 /* CUDA-event timing of the contraction kernel launches of local device 0 (for the roofline line of bench.py). */
 int speigen_solver_kernel_timing(speigen_solver* s, int32_t enable);
 int speigen_solver_kernel_time(speigen_solver* s, double* ms_total, int32_t* launches);

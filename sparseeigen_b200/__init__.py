@@ -41,7 +41,7 @@ class Cfg(C.Structure):
         ("tol_factor", C.c_double), ("backtrack_slack", C.c_double), ("rank_tol", C.c_double), ("pd_tol", C.c_double),
         ("max_backtracks", C.c_int32), ("init_max_passes", C.c_int32), ("init_tol", C.c_double),
         ("init_block", C.c_int32), ("init_seed", C.c_uint64), ("check_symmetric", C.c_int32), ("check_na", C.c_int32),
-        ("n_gpus", C.c_int32), ("first_device", C.c_int32), ("fused_epilogue", C.c_int32), ("verbose", C.c_int32), ("pd_check_passes", C.c_int32),
+        ("n_gpus", C.c_int32), ("first_device", C.c_int32), ("fused_epilogue", C.c_int32), ("verbose", C.c_int32), ("pd_check_passes", C.c_int32), ("p2p_exchange", C.c_int32),
     ]
 
 
@@ -111,6 +111,7 @@ def lib():
     L.speigen_solver_load_device_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]
     L.speigen_solver_mm_steps.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, _dp, C.POINTER(C.c_float)]
     L.speigen_solver_sync.argtypes = [C.c_void_p]
+    L.speigen_solver_exchange_mode.argtypes = [C.c_void_p]
     L.speigen_solver_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
     L.speigen_solver_kernel_time.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int32)]
     _lib = L
@@ -385,6 +386,9 @@ class Solver:
         ms = C.c_float(0.0)
         _check(self.L.speigen_solver_mm_steps(self.h, nsteps, stage, float(rho), _ptr(dd), C.byref(ms) if timed else None))
         return ms.value if timed else None
+
+    def exchange_mode(self) -> str:
+        return {0: "none", 1: "nccl", 2: "p2p-fused"}[self.L.speigen_solver_exchange_mode(self.h)]
 
     def sync(self):
         _check(self.L.speigen_solver_sync(self.h))

@@ -46,6 +46,7 @@ void speigen_cfg_default(speigen_cfg* c) {
   c->fused_epilogue = 1;
   c->verbose = 0;
   c->pd_check_passes = 4;
+  c->p2p_exchange = 1;
 }
 
 const char* speigen_last_error(void) { return last_error(); }
@@ -293,6 +294,7 @@ int speigen_solver_mm_steps(speigen_solver* s, int32_t nsteps, int32_t stage, do
   return s->impl.mm_steps(nsteps, stage, rho, d, ms_out);
 }
 int speigen_solver_sync(speigen_solver* s) { return s->impl.sync_all(); }
+int speigen_solver_exchange_mode(speigen_solver* s) { return s->impl.prob.world <= 1 ? 0 : (s->impl.p2p ? 2 : 1); }
 int speigen_solver_kernel_timing(speigen_solver* s, int32_t enable) { s->impl.enable_kernel_timing(enable != 0); return SPEIGEN_OK; }
 int speigen_solver_kernel_time(speigen_solver* s, double* ms_total, int32_t* launches) {
   int n = 0;

@@ -57,7 +57,14 @@ __device__ __forceinline__ void epi_pair(const KParams& prm, const double* s_d, 
   if (jl >= prm.rows || c0 >= prm.ncr) return;
   const size_t roff = static_cast<size_t>(ep.row_off + jl) * ep.pitch;
   const bool has1 = (c0 + 1) < prm.ncr;
-  if (ep.Y) {
+  if (ep.npeers > 0) {
+    if (ep.peerY[0]) {
+      for (int p = 0; p < ep.npeers; ++p) {
+        if (has1) *reinterpret_cast<double2*>(ep.peerY[p] + roff + c0) = make_double2(y0, y1);
+        else ep.peerY[p][roff + c0] = y0;
+      }
+    }
+  } else if (ep.Y) {
     if (has1) *reinterpret_cast<double2*>(ep.Y + roff + c0) = make_double2(y0, y1);
     else ep.Y[roff + c0] = y0;
   }
@@ -67,21 +74,30 @@ __device__ __forceinline__ void epi_pair(const KParams& prm, const double* s_d, 
   else v0 = ep.V[roff + c0];
   if (ep.cplx) {
     const int cc = c0 >> 1;
-    if (ep.B) {
+    if (ep.B || ep.peerB[0]) {
       const double t = weight_of_abs(hypot(v0, v1), ep.sc) - s_wmax[cc];
-      *reinterpret_cast<double2*>(ep.B + roff + c0) =
-          make_double2(s_d[cc] * y0 - t * v0 * s_rho[cc], s_d[cc] * y1 - t * v1 * s_rho[cc]);
+      const double2 bb = make_double2(s_d[cc] * y0 - t * v0 * s_rho[cc], s_d[cc] * y1 - t * v1 * s_rho[cc]);
+      if (ep.npeers > 0) { for (int p = 0; p < ep.npeers; ++p) *reinterpret_cast<double2*>(ep.peerB[p] + roff + c0) = bb; }
+      else *reinterpret_cast<double2*>(ep.B + roff + c0) = bb;
     }
     ds0 += v0 * y0 + v1 * y1;
   } else {
-    if (ep.B) {
+    if (ep.B || ep.peerB[0]) {
       const double t0 = weight_of_abs(fabs(v0), ep.sc) - s_wmax[c0];
       const double b0 = s_d[c0] * y0 - t0 * v0 * s_rho[c0];
+      double b1 = 0.0;
       if (has1) {
         const double t1 = weight_of_abs(fabs(v1), ep.sc) - s_wmax[c0 + 1];
-        *reinterpret_cast<double2*>(ep.B + roff + c0) = make_double2(b0, s_d[c0 + 1] * y1 - t1 * v1 * s_rho[c0 + 1]);
+        b1 = s_d[c0 + 1] * y1 - t1 * v1 * s_rho[c0 + 1];
+      }
+      if (ep.npeers > 0) {
+        for (int p = 0; p < ep.npeers; ++p) {
+          if (has1) *reinterpret_cast<double2*>(ep.peerB[p] + roff + c0) = make_double2(b0, b1);
+          else ep.peerB[p][roff + c0] = b0;
+        }
       } else {
-        ep.B[roff + c0] = b0;
+        if (has1) *reinterpret_cast<double2*>(ep.B + roff + c0) = make_double2(b0, b1);
+        else ep.B[roff + c0] = b0;
       }
     }
     ds0 += v0 * y0;
@@ -202,6 +218,34 @@ k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
     named_bar_sync(1, NCW * 32);
   };
 
+  // fused exchange: after this CTA's last store, the CTA that finishes last (grid-wide) publishes the rank's dot sums
+  // and raises the epoch flag on every peer.  fence.sys + counter make all peer stores of all CTAs visible first.
+  auto finish_exchange = [&]() {
+    if (prm.epi.npeers == 0) return;
+    __threadfence_system();
+    named_bar_sync(1, NCW * 32);
+    if (ctid == 0) {
+      const int old = atomicAdd(prm.epi.done_count, 1);
+      const int last = (old == static_cast<int>(gridDim.x) - 1);
+      if (last) *prm.epi.done_count = 0;
+      s_last = last;
+    }
+    named_bar_sync(1, NCW * 32);
+    if (!s_last) return;
+    __threadfence_system();
+    if (want_dots && ctid < nout) {          // this rank's column dots: fixed-order sum over its row tiles
+      double s = 0.0;
+      for (int t = 0; t < prm.n_row_tiles; ++t) s += __ldcg(prm.epi.dots + static_cast<size_t>(t) * nout + ctid);
+      for (int p = 0; p < prm.epi.npeers; ++p) prm.epi.peer_dots[p][prm.epi.my_shard * nout + ctid] = s;
+    }
+    __threadfence_system();
+    named_bar_sync(1, NCW * 32);
+    if (ctid < prm.epi.npeers) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(prm.epi.peer_flag[ctid] + prm.epi.my_shard) = prm.epi.epoch;
+    }
+  };
+
   if (RF > 0 && warp >= kConsumerWarps) {
     // ================================ DFMA warps ================================
     const int fw = warp - kConsumerWarps;        // 0..3, rows [64 fw, 64 fw + 64)
@@ -320,6 +364,7 @@ k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
         }
       }
     }
+    finish_exchange();
     return;
   }
 
@@ -437,6 +482,28 @@ k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
 #pragma unroll
       for (int nt = 0; nt < NTD; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
   }
+  finish_exchange();
+}
+
+// consumer side of the fused exchange
+__global__ void __launch_bounds__(256) k_exchange_wait_copy(const unsigned long long* flags, int world, unsigned long long epoch,
+                                                            const double* srcY, double* dstY, const double* srcB, double* dstB,
+                                                            size_t panel_doubles, const double* src_dots, double* dst_dots,
+                                                            int ndots) {
+  if (threadIdx.x < world) {
+    const volatile unsigned long long* f = flags + threadIdx.x;
+    while (*f < epoch) { __nanosleep(64); }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const size_t n2 = panel_doubles / 2;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    if (srcY) reinterpret_cast<double2*>(dstY)[i] = __ldcv(reinterpret_cast<const double2*>(srcY) + i);
+    if (srcB) reinterpret_cast<double2*>(dstB)[i] = __ldcv(reinterpret_cast<const double2*>(srcB) + i);
+  }
+  if (src_dots && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < ndots; i += blockDim.x) dst_dots[i] = __ldcv(src_dots + i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -794,6 +861,15 @@ int launch_contract_std(const StreamMat& A, const double* P, int ncr, const EpiA
     case 7 * 8 + 4: return launch_std_nt<7, 4>(A, prm, grid, smem, stream);
     default: return launch_std_nt<8, 0>(A, prm, grid, smem, stream);
   }
+}
+
+int launch_exchange_wait_copy(const unsigned long long* flags, int world, unsigned long long epoch, const double* srcY,
+                              double* dstY, const double* srcB, double* dstB, size_t panel_doubles, const double* src_dots,
+                              double* dst_dots, int ndots, cudaStream_t stream) {
+  k_exchange_wait_copy<<<148, 256, 0, stream>>>(flags, world, epoch, srcY, dstY, srcB, dstB, panel_doubles, src_dots, dst_dots, ndots);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
 }
 
 int launch_contract_tr(const StreamMat& A, const double* P, int ncr, double* T, int t_pitch, const ContractWorkspace& ws,

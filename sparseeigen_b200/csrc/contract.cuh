@@ -33,6 +33,17 @@ struct EpiArgs {
   int cplx = 0;
   int pitch = 0;                   // panel pitch (doubles)
   int64_t row_off = 0;             // global row of local output row 0 (row-sharded covariance)
+  // ---- fused exchange (row-sharded covariance, P > 1): the epilogue stores its row block straight into every GPU's
+  // exchange buffer over NVLink (peer pointers, own GPU included) instead of a local store + NCCL allgather; the CTA
+  // that finishes last publishes this rank's column-dot sums and raises an epoch flag on every peer.
+  int npeers = 0;                  // 0 = local stores only
+  int my_shard = 0;
+  double* peerY[8] = {};           // exchange slot for Y on each GPU (as mapped into this GPU's address space)
+  double* peerB[8] = {};
+  double* peer_dots[8] = {};       // [world][q] on each GPU
+  unsigned long long* peer_flag[8] = {};   // [world] epoch flags on each GPU
+  unsigned long long epoch = 0;
+  int* done_count = nullptr;       // CTA completion counter (self-resetting)
 };
 
 struct ContractWorkspace {
@@ -49,6 +60,7 @@ constexpr int kTK = 16 * kNBox;    // contracted doubles per stage
 constexpr int kConsumerWarps = 8;
 constexpr int kMT = kTJ / (8 * kConsumerWarps);   // m-tiles (8 rows) per warp = 4
 constexpr int kThreads = kConsumerWarps * 32 + 32;
+constexpr int kMaxPeers = 8;
 
 int make_stream_mat(StreamMat* sm, const double* ptr, int64_t rows, int64_t kd, int64_t ld, int box_rows);
 
@@ -63,5 +75,11 @@ size_t contract_slot_doubles(int ncr);
 int launch_contract_tr(const StreamMat& A, const double* P, int ncr, double* T, int t_pitch,
                        const ContractWorkspace& ws, int num_sms, cudaStream_t stream);
 size_t contract_tr_workspace_slots(int64_t kd, int num_sms);
+
+// Consumer side of the fused exchange: wait until every rank's epoch flag has arrived, then copy the exchange slots
+// (panel rows [0, rows) and the per-rank dot sums) into their destination buffers.
+int launch_exchange_wait_copy(const unsigned long long* flags, int world, unsigned long long epoch, const double* srcY,
+                              double* dstY, const double* srcB, double* dstB, size_t panel_doubles, const double* src_dots,
+                              double* dst_dots, int ndots, cudaStream_t stream);
 
 }  // namespace speigen

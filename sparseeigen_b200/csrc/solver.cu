@@ -185,6 +185,17 @@ int Solver::alloc_dev(Dev& d) {
   const size_t ntiles = static_cast<size_t>((d.a_rows + kTJ - 1) / kTJ) + 1;
   SPE_CUDA(cudaMalloc(&d.dots_part, std::max<size_t>(ntiles, kPanelBlocks) * kMaxCols * sizeof(double)));
   SPE_CUDA(cudaMalloc(&d.dots_gather, static_cast<size_t>(prob.world) * kMaxCols * sizeof(double)));
+  if (!data && prob.world > 1 && prob.world <= kMaxPeers) {
+    const size_t xb_bytes = 4 * pbytes;
+    SPE_CUDA(cudaMalloc(&d.xb, xb_bytes));
+    SPE_CUDA(cudaMemsetAsync(d.xb, 0, xb_bytes, d.st));
+    SPE_CUDA(cudaMalloc(&d.xdots, 2 * static_cast<size_t>(prob.world) * kMaxCols * sizeof(double)));
+    SPE_CUDA(cudaMemsetAsync(d.xdots, 0, 2 * static_cast<size_t>(prob.world) * kMaxCols * sizeof(double), d.st));
+    SPE_CUDA(cudaMalloc(&d.xflags, kMaxPeers * sizeof(unsigned long long)));
+    SPE_CUDA(cudaMemsetAsync(d.xflags, 0, kMaxPeers * sizeof(unsigned long long), d.st));
+    SPE_CUDA(cudaMalloc(&d.done_count, sizeof(int)));
+    SPE_CUDA(cudaMemsetAsync(d.done_count, 0, sizeof(int), d.st));
+  }
   SPE_CUDA(cudaMalloc(&d.scal, 512 * sizeof(double)));
   SPE_CUDA(cudaMemsetAsync(d.scal, 0, 512 * sizeof(double), d.st));
   SPE_CUDA(cudaMalloc(&d.vecm, static_cast<size_t>(2 * m + 16) * sizeof(double)));
@@ -199,10 +210,11 @@ void Solver::destroy() {
   for (Dev& d : devs) {
     cudaSetDevice(d.ordinal);
     if (d.st) cudaStreamSynchronize(d.st);
+    for (int i = 0; i < d.n_ipc_opened; ++i) cudaIpcCloseMemHandle(d.ipc_opened[i]);
     if (d.comm && nccl_api()) nccl_api()->CommDestroy(d.comm);
     void* ptrs[] = {d.A, d.hat, d.Tdata, d.gather, d.ws.partials, d.ws.counters, d.ps.gram_part, d.gram_part2,
                     d.ps.col_part, d.ps.ticket, d.absmin_a, d.absmin_b, d.Msmall, d.evals, d.warm, d.status, d.dvec, d.rho,
-                    d.dots_part, d.dots_gather, d.scal, d.vecm, d.vecm2, d.scan_part, d.out_cm, d.flush};
+                    d.dots_part, d.dots_gather, d.scal, d.vecm, d.vecm2, d.scan_part, d.out_cm, d.flush, d.xb, d.xdots, d.xflags, d.done_count};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     for (int b = 0; b < NBUF; ++b)
@@ -228,7 +240,7 @@ int Solver::init_comm_all() {
   SPE_NCCL(nc->CommInitAll(comms.data(), static_cast<int>(devs.size()), ords.data()));
   for (size_t i = 0; i < devs.size(); ++i) devs[i].comm = comms[i];
   comm_ready = true;
-  return SPEIGEN_OK;
+  return init_p2p();
 }
 
 int Solver::init_comm_rank(const void* id128) {
@@ -244,6 +256,75 @@ int Solver::init_comm_rank(const void* id128) {
   }
   SPE_NCCL(nc->GroupEnd());
   comm_ready = true;
+  return init_p2p();
+}
+
+// Map every shard's exchange buffers into every local device: direct peer access inside one process, CUDA IPC
+// handles (allgathered over the NCCL communicator) across processes.  Any failure leaves the NCCL allgather path on.
+int Solver::init_p2p() {
+  p2p = false;
+  if (prob.world <= 1 || data || !cfg.p2p_exchange || prob.world > kMaxPeers) return SPEIGEN_OK;
+  if (rows_per_shard * (prob.world - 1) >= m) return SPEIGEN_OK;   // an empty shard would never raise its flag
+  const bool single_process = static_cast<int>(devs.size()) == prob.world;
+  if (single_process) {
+    for (Dev& a : devs) {
+      if (cudaSetDevice(a.ordinal) != cudaSuccess) return SPEIGEN_OK;
+      for (Dev& b : devs) {
+        if (&a != &b) {
+          int can = 0;
+          if (cudaDeviceCanAccessPeer(&can, a.ordinal, b.ordinal) != cudaSuccess || !can) { cudaGetLastError(); return SPEIGEN_OK; }
+          const cudaError_t e = cudaDeviceEnablePeerAccess(b.ordinal, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return SPEIGEN_OK; }
+          cudaGetLastError();
+        }
+        a.peer_xb[b.shard] = b.xb;
+        a.peer_xdots[b.shard] = b.xdots;
+        a.peer_xflags[b.shard] = b.xflags;
+      }
+    }
+    p2p = true;
+    return SPEIGEN_OK;
+  }
+  // one process per GPU: exchange IPC handles through the communicator (3 handles of 64 bytes per rank)
+  const NcclApi* nc = nccl_api();
+  if (!nc || devs.size() != 1) return SPEIGEN_OK;
+  Dev& d = devs[0];
+  SPE_CUDA(cudaSetDevice(d.ordinal));
+  cudaIpcMemHandle_t mine[3];
+  if (cudaIpcGetMemHandle(&mine[0], d.xb) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], d.xdots) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine[2], d.xflags) != cudaSuccess) { cudaGetLastError(); return SPEIGEN_OK; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+  const size_t per = 3 * 64 / sizeof(double);
+  double* dev_h = nullptr;
+  SPE_CUDA(cudaMalloc(&dev_h, per * prob.world * sizeof(double)));
+  SPE_CUDA(cudaMemcpyAsync(dev_h + per * d.shard, mine, 3 * 64, cudaMemcpyHostToDevice, d.st));
+  SPE_NCCL(nc->AllGather(dev_h + per * d.shard, dev_h, per, NCCL_DOUBLE, d.comm, d.st));
+  std::vector<cudaIpcMemHandle_t> all(3 * prob.world);
+  SPE_CUDA(cudaMemcpyAsync(all.data(), dev_h, 3 * 64 * prob.world, cudaMemcpyDeviceToHost, d.st));
+  SPE_CUDA(cudaStreamSynchronize(d.st));
+  cudaFree(dev_h);
+  bool ok = true;
+  for (int r = 0; r < prob.world && ok; ++r) {
+    if (r == d.shard) { d.peer_xb[r] = d.xb; d.peer_xdots[r] = d.xdots; d.peer_xflags[r] = d.xflags; continue; }
+    void* ptr[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3 && ok; ++k) {
+      if (cudaIpcOpenMemHandle(&ptr[k], all[3 * r + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      d.ipc_opened[d.n_ipc_opened++] = ptr[k];
+    }
+    d.peer_xb[r] = static_cast<double*>(ptr[0]);
+    d.peer_xdots[r] = static_cast<double*>(ptr[1]);
+    d.peer_xflags[r] = static_cast<unsigned long long*>(ptr[2]);
+  }
+  // every rank must agree, otherwise some would wait for flags that never come
+  double agree = ok ? 1.0 : 0.0;
+  double* dflag = nullptr;
+  SPE_CUDA(cudaMalloc(&dflag, sizeof(double)));
+  SPE_CUDA(cudaMemcpyAsync(dflag, &agree, sizeof(double), cudaMemcpyHostToDevice, d.st));
+  SPE_NCCL(nc->AllReduce(dflag, dflag, 1, NCCL_DOUBLE, NCCL_SUM, d.comm, d.st));
+  SPE_CUDA(cudaMemcpyAsync(&agree, dflag, sizeof(double), cudaMemcpyDeviceToHost, d.st));
+  SPE_CUDA(cudaStreamSynchronize(d.st));
+  cudaFree(dflag);
+  p2p = (agree == static_cast<double>(prob.world));
   return SPEIGEN_OK;
 }
 
@@ -427,6 +508,8 @@ int Solver::op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vep
   const NcclApi* nc = multi ? nccl_api() : nullptr;
   if (multi && !nc) return SPEIGEN_ERR_NCCL;
   const bool post_unfused = data && multi;   // partial sums need the exchange before any epilogue math
+  const bool use_p2p = p2p && multi && !data;
+  const int parity = static_cast<int>(epoch & 1);
   for (Dev& d : devs) {
     SPE_CUDA(cudaSetDevice(d.ordinal));
     const double* operand = d.buf[in];
@@ -454,6 +537,23 @@ int Solver::op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vep
       if (want_b || want_dots) ep.V = d.buf[vepi];
       if (want_dots) ep.dots = d.dots_part;
     }
+    if (use_p2p) {
+      // epilogue stores go to the exchange slots of every GPU (own one included); local Y/B/dots are filled by the waiter
+      const size_t slot = static_cast<size_t>(mrows) * pdb.pitch;
+      double* const loc_y = ep.Y;
+      double* const loc_b = ep.B;
+      ep.npeers = prob.world;
+      ep.my_shard = d.shard;
+      for (int r = 0; r < prob.world; ++r) {
+        double* base = d.peer_xb[r] + (parity * 2) * slot;
+        ep.peerY[r] = loc_y ? base : nullptr;
+        ep.peerB[r] = loc_b ? base + slot : nullptr;
+        ep.peer_dots[r] = d.peer_xdots[r] + static_cast<size_t>(parity) * prob.world * kMaxCols;
+        ep.peer_flag[r] = d.peer_xflags[r];
+      }
+      ep.epoch = epoch + 1;
+      ep.done_count = d.done_count;
+    }
     const bool tme = ktiming && (&d == &devs[0]) && kev_used + 2 <= kev.size();
     if (tme) SPE_CUDA(cudaEventRecord(kev[kev_used], d.st));
     SPE_TRY(launch_contract_std(d.Astd, operand, pd.ncr, ep, d.ws, d.num_sms, d.st));
@@ -463,6 +563,22 @@ int Solver::op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vep
   const int nout = pd.q;
   if (!multi) {
     n_dot_parts = static_cast<int>((devs[0].a_rows + kTJ - 1) / kTJ);
+    return SPEIGEN_OK;
+  }
+  if (use_p2p) {
+    ++epoch;
+    const size_t slot = static_cast<size_t>(mrows) * pdb.pitch;
+    const size_t nd = static_cast<size_t>(padded_rows(m)) * pd.pitch;   // doubles actually used by this panel shape
+    for (Dev& d : devs) {
+      SPE_CUDA(cudaSetDevice(d.ordinal));
+      const double* sy = want_y ? d.xb + (parity * 2) * slot : nullptr;
+      const double* sb = want_b ? d.xb + (parity * 2 + 1) * slot : nullptr;
+      SPE_TRY(launch_exchange_wait_copy(d.xflags, prob.world, epoch, sy, want_y ? d.buf[outY] : nullptr, sb,
+                                        want_b ? d.buf[outB] : nullptr, std::max(nd, static_cast<size_t>(rows_per_shard) * prob.world * pd.pitch),
+                                        want_dots ? d.xdots + static_cast<size_t>(parity) * prob.world * kMaxCols : nullptr,
+                                        d.dots_part, prob.world * nout, d.st));
+    }
+    if (want_dots) n_dot_parts = prob.world;
     return SPEIGEN_OK;
   }
   if (!data) {

@@ -54,6 +54,16 @@ struct Dev {
   double* out_cm = nullptr;    // column-major staging for D2H (m*q*(1+cplx))
   double* flush = nullptr;     // L2 flush buffer (timing only)
   ncclComm_t comm = nullptr;
+  // fused P2P exchange (row-sharded covariance)
+  double* xb = nullptr;                    // [2 parities][2 slots (Y, B)][mrows * pitch_b]
+  double* xdots = nullptr;                 // [2 parities][world][kMaxCols]
+  unsigned long long* xflags = nullptr;    // [world] epoch flags written by the peers
+  int* done_count = nullptr;
+  double* peer_xb[kMaxPeers] = {};         // the same buffers of every shard as mapped into this device
+  double* peer_xdots[kMaxPeers] = {};
+  unsigned long long* peer_xflags[kMaxPeers] = {};
+  void* ipc_opened[3 * kMaxPeers] = {};
+  int n_ipc_opened = 0;
 };
 
 class Solver {
@@ -105,6 +115,9 @@ class Solver {
   void enable_kernel_timing(bool on);
   int kernel_time(double* ms_total, int* launches);
   int exchange_allgather(Buf b, const PanelDims& pd);
+  int init_p2p();
+  bool p2p = false;
+  unsigned long long epoch = 0;   // contraction counter of the fused exchange (identical on every rank)
 
  private:
   int alloc_dev(Dev& d);

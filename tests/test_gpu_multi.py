@@ -30,11 +30,15 @@ def test_contract_sharded_matches_single(P):
     m, q = 1037, 20
     A = rng.standard_normal((m, m)); S = (A + A.T) / 2
     U = rng.standard_normal((m, q))
-    with sb.Solver(m, q, world=P, local_gpus=P) as s:
-        s.init_comm(None)
-        s.load(S)
-        Y = s.contract(U)
-    assert np.linalg.norm(Y - S @ U) / np.linalg.norm(S @ U) < 1e-13
+    Ys = []
+    for p2p in (1, 0):       # fused peer-store exchange vs NCCL allgather: same bits
+        with sb.Solver(m, q, world=P, local_gpus=P, p2p_exchange=p2p) as s:
+            s.init_comm(None)
+            s.load(S)
+            Ys.append(s.contract(U))
+            Ys.append(s.contract(U))
+    assert np.linalg.norm(Ys[0] - S @ U) / np.linalg.norm(S @ U) < 1e-13
+    assert np.array_equal(Ys[0], Ys[1]) and np.array_equal(Ys[0], Ys[2]) and np.array_equal(Ys[0], Ys[3])
     n = 911
     X = rng.standard_normal((n, m)) + 1j * rng.standard_normal((n, m))
     Uc = rng.standard_normal((m, 5)) + 1j * rng.standard_normal((m, 5))
@@ -52,6 +56,8 @@ def test_e2e_two_gpus_matches_one():
     S = o.sample_cov(X)
     a = sb.spEigen(S, 5, n_gpus=1)
     b = sb.spEigen(S, 5, n_gpus=2)
+    b0 = sb.spEigen(S, 5, n_gpus=2, p2p_exchange=0)
+    assert np.array_equal(b["vectors"], b0["vectors"]) and np.array_equal(b["info"]["F"], b0["info"]["F"])
     n = min(len(a["info"]["F"]), len(b["info"]["F"]), 10)
     assert np.allclose(a["info"]["F"][:n], b["info"]["F"][:n], rtol=1e-11)
     assert np.array_equal(a["vectors"] != 0, b["vectors"] != 0)
