@@ -327,12 +327,6 @@ __global__ void __launch_bounds__(kPT) k_absmin(const double* V, int64_t m, int 
     absmin_part[static_cast<size_t>(gridDim.x) * kMaxCols + threadIdx.x] = min_parts_ilp(absmin_part + threadIdx.x, gridDim.x, kMaxCols);
 }
 
-__global__ void k_wmax(const double* absmin_part, int nparts, int q, StageConsts sc, double* wmax) {
-  const int c = threadIdx.x;
-  if (c >= q) return;
-  wmax[c] = weight_of_abs(min_parts_ilp(absmin_part + c, nparts, kMaxCols), sc);
-}
-
 // ------------------------------------------------------------------------------------------------
 // block-level fixed-order sum of one value per thread (all threads get nothing; result in s_out by thread 0)
 __device__ __forceinline__ double block_sum_fixed(double v, double* s_buf) {
@@ -1106,13 +1100,6 @@ int launch_extrapolate(const PanelDims& pd, const double* V, const double* V1, c
 int launch_absmin(const PanelDims& pd, const double* V, double* absmin_part, int* ticket, cudaStream_t st) {
   if (pd.cplx) k_absmin<true><<<kPanelBlocks, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, absmin_part, ticket);
   else k_absmin<false><<<kPanelBlocks, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, absmin_part, ticket);
-  SPE_CUDA(cudaGetLastError());
-  note_launch(1);
-  return SPEIGEN_OK;
-}
-
-int launch_wmax(const PanelDims& pd, const double* absmin_part, StageConsts sc, double* wmax, cudaStream_t st) {
-  k_wmax<<<1, kMaxCols, 0, st>>>(absmin_part, kPanelBlocks, pd.q, sc, wmax);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

@@ -54,7 +54,6 @@ int launch_extrapolate(const PanelDims& pd, const double* V, const double* V1, c
 // absmin_part: [kPanelBlocks + 1][kMaxCols]; the last row receives the final column minima (last-block reduction)
 int launch_absmin(const PanelDims& pd, const double* V, double* absmin_part, int* ticket, cudaStream_t st);
 inline const double* absmin_final(const double* absmin_part) { return absmin_part + static_cast<size_t>(kPanelBlocks) * kMaxCols; }
-int launch_wmax(const PanelDims& pd, const double* absmin_part, StageConsts sc, double* wmax, cudaStream_t st);
 // norms[0..1] = {||V1 - V||_F, ||V2 - 2 V1 + V||_F}
 int launch_squarem_norms(const PanelDims& pd, const double* V, const double* V1, const double* V2,
                          const PanelScratch& sc, double* norms, cudaStream_t st);

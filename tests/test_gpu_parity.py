@@ -63,6 +63,21 @@ def test_contract_data(n, m, q, cplx):
         assert rel(s.contract(U), np.conj(X.T) @ (X @ U)) < 1e-13
 
 
+def test_contract_hybrid_dfma_variant(monkeypatch):
+    """The opt-in <NTF, RF=4> variant (left-over columns on dedicated DFMA warps) computes the same product."""
+    rng = np.random.default_rng(9)
+    for m, q in ((1300, 20), (700, 3), (900, 12)):
+        S = herm(rng, m, False)
+        U = panel(rng, m, q, False)
+        with sb.Solver(m, q) as s:
+            s.load(S)
+            Y0 = s.contract(U)
+            monkeypatch.setenv("SPEIGEN_HYBRID_DFMA", "1")
+            Y1 = s.contract(U)
+            monkeypatch.delenv("SPEIGEN_HYBRID_DFMA")
+        assert rel(Y0, S @ U) < 1e-13 and rel(Y1, S @ U) < 1e-13
+
+
 def test_contract_is_deterministic_and_linear():
     rng = np.random.default_rng(1)
     m, q = 4000, 20
