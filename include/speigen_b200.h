@@ -102,6 +102,8 @@ int speigen_run_c64(const double* X_interleaved, int64_t nrow, int64_t ncol, int
                     const double* d, const double* V0_interleaved, double thres, const speigen_cfg* cfg,
                     speigen_out* out);
 
+/* Releases the device context the one-shot calls keep alive between calls of the same (small) shape. */
+int speigen_shutdown(void);
 const char* speigen_last_error(void);
 int speigen_abi_version(void);
 int speigen_device_count(void);

@@ -76,6 +76,8 @@ def lib():
                           f"or `make -C sparseeigen_b200/csrc`; there is no CPU fallback")
     L = C.CDLL(path, mode=C.RTLD_GLOBAL)
     L.speigen_last_error.restype = C.c_char_p
+    import atexit
+    atexit.register(L.speigen_shutdown)
     L.speigen_cfg_default.argtypes = [C.POINTER(Cfg)]
     L.speigen_run_f64.argtypes = [_dp, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, _dp, _dp, C.c_double,
                                   C.POINTER(Cfg), C.POINTER(Out)]

@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -304,6 +305,15 @@ int speigen_solver_kernel_time(speigen_solver* s, double* ms_total, int32_t* lau
 }
 
 // ---- one-shot drop-in calls -------------------------------------------------------------------
+static speigen_solver* g_cached = nullptr;
+static speigen_problem g_cached_prob;
+static speigen_cfg g_cached_cfg;
+
+int speigen_shutdown(void) {
+  if (g_cached) { speigen_solver_destroy(g_cached); g_cached = nullptr; }
+  return SPEIGEN_OK;
+}
+
 static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data, int is_complex, double q, double rho,
                        const double* d, const double* V0, double thres, const speigen_cfg* cfg_in, speigen_out* out) {
   if (!X || !out) { set_error("null argument"); return SPEIGEN_ERR_ARG; }
@@ -321,16 +331,37 @@ static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data,
   pb.world = cfg.n_gpus > 0 ? cfg.n_gpus : 1;
   pb.rank = 0;
   pb.local_gpus = pb.world;
+  // Small problems are latency-bound: creating/destroying the device context costs more than the solve (~7 of 16 ms at
+  // m <= 800), so one solver of the last shape is kept alive between calls (<= 1 GB of device memory; speigen_shutdown()
+  // or process exit releases it).  R calls are single-threaded; a mutex keeps other hosts safe.
+  static std::mutex mtx;
+  std::lock_guard<std::mutex> lock(mtx);
+  const size_t e = is_complex ? 2 : 1;
+  const size_t mat_bytes = static_cast<size_t>(nrow) * ncol * e * sizeof(double);
+  const bool cacheable = mat_bytes <= (256u << 20);
   speigen_solver* s = nullptr;
-  API_TRY(speigen_solver_create(&s, &pb, &cfg));
-  int rc = s->impl.init_comm_all();
+  if (g_cached && cacheable && std::memcmp(&g_cached_prob, &pb, sizeof(pb)) == 0 && std::memcmp(&g_cached_cfg, &cfg, sizeof(cfg)) == 0) {
+    s = g_cached;
+    g_cached = nullptr;
+    s->impl.reset_for_reuse();
+  } else {
+    if (g_cached) { speigen_solver_destroy(g_cached); g_cached = nullptr; }
+    API_TRY(speigen_solver_create(&s, &pb, &cfg));
+  }
+  int rc = s->impl.comm_ready ? SPEIGEN_OK : s->impl.init_comm_all();
   const double t0 = wall_s();
   if (rc == SPEIGEN_OK) rc = s->impl.load_host(X);
   out->seconds_upload = wall_s() - t0;
   if (rc == SPEIGEN_OK) rc = s->impl.prepare();
   if (rc == SPEIGEN_OK) rc = s->impl.init_vectors(V0, out);
   if (rc == SPEIGEN_OK) rc = s->impl.run(rho, d, thres, out);
-  speigen_solver_destroy(s);
+  if (rc == SPEIGEN_OK && cacheable) {
+    g_cached = s;
+    g_cached_prob = pb;
+    g_cached_cfg = cfg;
+  } else {
+    speigen_solver_destroy(s);
+  }
   return rc;
 }
 

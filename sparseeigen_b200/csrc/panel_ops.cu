@@ -135,7 +135,7 @@ struct ApplyArgs {
   double* absmin_part;   // [kPanelBlocks + 1][kMaxCols]; the last row receives the final column minima
   int* ticket;
   int64_t m;
-  int q, ncr, pitch, cplx;
+  int q, ncr, pitch, cplx, nblk;
 };
 
 template <int NT, bool GRAM>
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kPT) k_apply_mma(const ApplyArgs p) {
       p.absmin_part[static_cast<size_t>(blockIdx.x) * kMaxCols + threadIdx.x] = v;
     }
     if (last_block_done(p.ticket) && threadIdx.x < p.q)
-      p.absmin_part[static_cast<size_t>(gridDim.x) * kMaxCols + threadIdx.x] = min_parts_ilp(p.absmin_part + threadIdx.x, gridDim.x, kMaxCols);
+      p.absmin_part[static_cast<size_t>(kPanelBlocks) * kMaxCols + threadIdx.x] = min_parts_ilp(p.absmin_part + threadIdx.x, gridDim.x, kMaxCols);
   }
   if (GRAM) {
     __syncthreads();
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kPT) k_absmin(const double* V, int64_t m, int 
     absmin_part[static_cast<size_t>(blockIdx.x) * kMaxCols + threadIdx.x] = amin;
   }
   if (last_block_done(ticket) && threadIdx.x < q)
-    absmin_part[static_cast<size_t>(gridDim.x) * kMaxCols + threadIdx.x] = min_parts_ilp(absmin_part + threadIdx.x, gridDim.x, kMaxCols);
+    absmin_part[static_cast<size_t>(kPanelBlocks) * kMaxCols + threadIdx.x] = min_parts_ilp(absmin_part + threadIdx.x, gridDim.x, kMaxCols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -992,11 +992,11 @@ inline int nblk(int64_t n, int t = 256) { return static_cast<int>((n + t - 1) / 
 int launch_gram(const PanelDims& pd, const double* A, const double* B, double* gram_part, cudaStream_t st) {
   const int nt = (pd.ncr + 7) / 8;
   switch (nt <= 5 ? nt : 4) {
-    case 1: k_gram_mma<1><<<kPanelBlocks, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
-    case 2: k_gram_mma<2><<<kPanelBlocks, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
-    case 3: k_gram_mma<3><<<kPanelBlocks, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
-    case 5: k_gram_mma<5><<<kPanelBlocks, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
-    default: k_gram_mma<4><<<kPanelBlocks, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
+    case 1: k_gram_mma<1><<<pd.nblk, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
+    case 2: k_gram_mma<2><<<pd.nblk, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
+    case 3: k_gram_mma<3><<<pd.nblk, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
+    case 5: k_gram_mma<5><<<pd.nblk, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
+    default: k_gram_mma<4><<<pd.nblk, kPT, 0, st>>>(A, B, pd.m, pd.ncr, pd.pitch, gram_part); break;
   }
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
@@ -1045,8 +1045,8 @@ static int launch_apply_nt(const ApplyArgs& pa, bool gram, cudaStream_t st) {
     SPE_CUDA(cudaFuncSetAttribute(k_apply_mma<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     set = true;
   }
-  if (gram) k_apply_mma<NT, true><<<kPanelBlocks, kPT, smem, st>>>(pa);
-  else k_apply_mma<NT, false><<<kPanelBlocks, kPT, smem, st>>>(pa);
+  if (gram) k_apply_mma<NT, true><<<pa.nblk, kPT, smem, st>>>(pa);
+  else k_apply_mma<NT, false><<<pa.nblk, kPT, smem, st>>>(pa);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;
@@ -1056,7 +1056,7 @@ int launch_apply(const PanelDims& pd, const double* A, const double* Msmall, dou
                  double* absmin_part_out, int* ticket, cudaStream_t st) {
   ApplyArgs pa{};
   pa.A = A; pa.Mh = Msmall; pa.Out = Out; pa.absmin_part = absmin_part_out; pa.ticket = ticket;
-  pa.m = pd.m; pa.q = pd.q; pa.ncr = pd.ncr; pa.pitch = pd.pitch; pa.cplx = pd.cplx;
+  pa.m = pd.m; pa.q = pd.q; pa.ncr = pd.ncr; pa.pitch = pd.pitch; pa.cplx = pd.cplx; pa.nblk = pd.nblk;
   const int nt = (pd.ncr + 7) / 8;
   const bool fuse = gram_part_out != nullptr && nt <= 5;   // Gram accumulators fit in registers
   pa.gram_part = fuse ? gram_part_out : nullptr;
@@ -1098,8 +1098,8 @@ int launch_extrapolate(const PanelDims& pd, const double* V, const double* V1, c
 }
 
 int launch_absmin(const PanelDims& pd, const double* V, double* absmin_part, int* ticket, cudaStream_t st) {
-  if (pd.cplx) k_absmin<true><<<kPanelBlocks, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, absmin_part, ticket);
-  else k_absmin<false><<<kPanelBlocks, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, absmin_part, ticket);
+  if (pd.cplx) k_absmin<true><<<pd.nblk, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, absmin_part, ticket);
+  else k_absmin<false><<<pd.nblk, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, absmin_part, ticket);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;
@@ -1107,7 +1107,7 @@ int launch_absmin(const PanelDims& pd, const double* V, double* absmin_part, int
 
 int launch_squarem_norms(const PanelDims& pd, const double* V, const double* V1, const double* V2,
                          const PanelScratch& sc, double* norms, cudaStream_t st) {
-  k_squarem_norms<<<kPanelBlocks, kPT, 0, st>>>(V, V1, V2, pd.m, pd.ncr, pd.pitch, sc.col_part, sc.ticket, norms);
+  k_squarem_norms<<<pd.nblk, kPT, 0, st>>>(V, V1, V2, pd.m, pd.ncr, pd.pitch, sc.col_part, sc.ticket, norms);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;
@@ -1116,10 +1116,10 @@ int launch_squarem_norms(const PanelDims& pd, const double* V, const double* V1,
 int launch_objective(const PanelDims& pd, const double* V0, StageConsts stc, const double* dots_part, int n_dot_parts,
                      const double* d, const double* rho, const PanelScratch& sc, double* out, cudaStream_t st) {
   if (pd.cplx)
-    k_objective<true><<<kPanelBlocks, kPT, 0, st>>>(V0, pd.m, pd.q, pd.pitch, stc, dots_part, n_dot_parts, d, rho,
+    k_objective<true><<<pd.nblk, kPT, 0, st>>>(V0, pd.m, pd.q, pd.pitch, stc, dots_part, n_dot_parts, d, rho,
                                                     sc.col_part, sc.ticket, out);
   else
-    k_objective<false><<<kPanelBlocks, kPT, 0, st>>>(V0, pd.m, pd.q, pd.pitch, stc, dots_part, n_dot_parts, d, rho,
+    k_objective<false><<<pd.nblk, kPT, 0, st>>>(V0, pd.m, pd.q, pd.pitch, stc, dots_part, n_dot_parts, d, rho,
                                                      sc.col_part, sc.ticket, out);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
@@ -1129,10 +1129,10 @@ int launch_objective(const PanelDims& pd, const double* V0, StageConsts stc, con
 int launch_finalize(const PanelDims& pd, const double* V, double thres, const PanelScratch& sc, double* norms_tmp,
                     double* out_colmajor, cudaStream_t st) {
   if (pd.cplx) {
-    k_thres_norms<true><<<kPanelBlocks, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, thres, sc.col_part, sc.ticket, norms_tmp);
+    k_thres_norms<true><<<pd.nblk, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, thres, sc.col_part, sc.ticket, norms_tmp);
     k_thres_scale_colmajor<true><<<nblk(pd.m * pd.q), 256, 0, st>>>(V, pd.m, pd.q, pd.pitch, thres, norms_tmp, out_colmajor);
   } else {
-    k_thres_norms<false><<<kPanelBlocks, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, thres, sc.col_part, sc.ticket, norms_tmp);
+    k_thres_norms<false><<<pd.nblk, kPT, 0, st>>>(V, pd.m, pd.q, pd.pitch, thres, sc.col_part, sc.ticket, norms_tmp);
     k_thres_scale_colmajor<false><<<nblk(pd.m * pd.q), 256, 0, st>>>(V, pd.m, pd.q, pd.pitch, thres, norms_tmp, out_colmajor);
   }
   SPE_CUDA(cudaGetLastError());
@@ -1172,8 +1172,8 @@ int launch_random_panel(const PanelDims& pd, uint64_t seed, double* P, cudaStrea
 }
 int launch_residual_norms(const PanelDims& pd, const double* ZW, const double* QW, const double* evals,
                           const PanelScratch& sc, double* out, cudaStream_t st) {
-  if (pd.cplx) k_residual_norms<true><<<kPanelBlocks, kPT, 0, st>>>(ZW, QW, evals, pd.m, pd.q, pd.pitch, sc.col_part, sc.ticket, out);
-  else k_residual_norms<false><<<kPanelBlocks, kPT, 0, st>>>(ZW, QW, evals, pd.m, pd.q, pd.pitch, sc.col_part, sc.ticket, out);
+  if (pd.cplx) k_residual_norms<true><<<pd.nblk, kPT, 0, st>>>(ZW, QW, evals, pd.m, pd.q, pd.pitch, sc.col_part, sc.ticket, out);
+  else k_residual_norms<false><<<pd.nblk, kPT, 0, st>>>(ZW, QW, evals, pd.m, pd.q, pd.pitch, sc.col_part, sc.ticket, out);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;
@@ -1199,8 +1199,8 @@ int launch_sum_panels(const PanelDims& pd, const double* In, int nparts, size_t 
 }
 
 int launch_coldots(const PanelDims& pd, const double* V, const double* Y, double* dots_part, cudaStream_t st) {
-  if (pd.cplx) k_coldots<true><<<kPanelBlocks, kPT, 0, st>>>(V, Y, pd.m, pd.q, pd.pitch, dots_part);
-  else k_coldots<false><<<kPanelBlocks, kPT, 0, st>>>(V, Y, pd.m, pd.q, pd.pitch, dots_part);
+  if (pd.cplx) k_coldots<true><<<pd.nblk, kPT, 0, st>>>(V, Y, pd.m, pd.q, pd.pitch, dots_part);
+  else k_coldots<false><<<pd.nblk, kPT, 0, st>>>(V, Y, pd.m, pd.q, pd.pitch, dots_part);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

@@ -16,10 +16,13 @@ struct PanelDims {
   int cplx = 0;
   int ncr = 0;         // real columns = q * (1 + cplx)
   int pitch = 0;       // doubles
+  int nblk = kPanelBlocks;   // stage-1 blocks actually launched for this panel (small m: fewer partials to sum)
 };
 inline PanelDims make_dims(int64_t m, int q, int cplx) {
   PanelDims d;
   d.m = m; d.q = q; d.cplx = cplx; d.ncr = q * (1 + cplx); d.pitch = panel_pitch(d.ncr);
+  const int64_t nb = (m + 127) / 128;
+  d.nblk = static_cast<int>(nb < 1 ? 1 : (nb > kPanelBlocks ? kPanelBlocks : nb));
   return d;
 }
 inline int64_t padded_rows(int64_t m) { return (m + kRowPad - 1) / kRowPad * kRowPad; }

@@ -90,6 +90,7 @@ int Solver::create(const speigen_problem* p, const speigen_cfg* c) {
   if (b > rank_cap) b = static_cast<int>(rank_cap);
   if (b < q) b = q;
   bq = b;
+  bq0 = b;
   if (bq * e > kMaxCols) {
     set_error("q = %d (%s) exceeds this build's limit of %d real columns per contraction", q, cplx ? "complex" : "real", kMaxCols);
     return SPEIGEN_ERR_UNSUPPORTED;
@@ -224,6 +225,21 @@ void Solver::destroy() {
   devs.clear();
   if (h_scal) cudaFreeHost(h_scal);
   h_scal = nullptr;
+}
+
+void Solver::reset_for_reuse() {
+  loaded = prepared = inited = false;
+  scale_max = 0.0;
+  sv2.clear();
+  contractions = 0;
+  n_dot_parts = 0;
+  bq = bq0;      // the initialiser may have shrunk its block on a rank-deficient input
+  pdb = make_dims(m, bq, cplx);
+  for (Dev& d : devs) {
+    cudaSetDevice(d.ordinal);
+    cudaMemsetAsync(d.status, 0, sizeof(int), d.st);
+    d.Astd.ptr = nullptr;
+  }
 }
 
 int Solver::init_comm_all() {
@@ -617,7 +633,7 @@ int Solver::op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vep
       SPE_TRY(launch_reweight(pd, ysum, d.buf[vepi], d.dvec, d.rho, d.wmax, sc, d.buf[outB], nullptr, d.st));
     if (want_dots) SPE_TRY(launch_coldots(pd, d.buf[vepi], ysum, d.dots_part, d.st));
   }
-  if (want_dots) n_dot_parts = kPanelBlocks;
+  if (want_dots) n_dot_parts = pd.nblk;
   return SPEIGEN_OK;
 }
 
@@ -627,9 +643,9 @@ int Solver::op_polar(Buf in, Buf out, const PanelDims& pd, bool have_gram, doubl
     SPE_CUDA(cudaSetDevice(d.ordinal));
     if (!have_gram) SPE_TRY(launch_gram(pd, d.buf[in], d.buf[in], d.ps.gram_part, d.st));
     double* warm = (warm_slot >= 0) ? d.warm + static_cast<size_t>(warm_slot) * kWarmStride : nullptr;
-    SPE_TRY(launch_small(pd, d.ps.gram_part, kPanelBlocks, SMALL_INVSQRT, d.Msmall, d.evals, d.status, warm, d.st));
+    SPE_TRY(launch_small(pd, d.ps.gram_part, pd.nblk, SMALL_INVSQRT, d.Msmall, d.evals, d.status, warm, d.st));
     SPE_TRY(launch_apply(pd, d.buf[in], d.Msmall, d.buf[BT2], d.gram_part2, nullptr, d.ps.ticket, d.st));
-    SPE_TRY(launch_small(pd, d.gram_part2, kPanelBlocks, SMALL_INVSQRT, d.Msmall, d.evals, d.status, nullptr, d.st));
+    SPE_TRY(launch_small(pd, d.gram_part2, pd.nblk, SMALL_INVSQRT, d.Msmall, d.evals, d.status, nullptr, d.st));
     double* am = which_absmin == 1 ? d.absmin_a : (which_absmin == 2 ? d.absmin_b : nullptr);
     SPE_TRY(launch_apply(pd, d.buf[BT2], d.Msmall, d.buf[out], nullptr, am, d.ps.ticket, d.st));
   }
@@ -669,7 +685,7 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
       for (Dev& d : devs) {
         SPE_CUDA(cudaSetDevice(d.ordinal));
         SPE_TRY(launch_gram(pdb, d.buf[BQ], d.buf[BZ], d.ps.gram_part, d.st));
-        SPE_TRY(launch_small(pdb, d.ps.gram_part, kPanelBlocks, SMALL_EIGVECS, d.Msmall, d.evals, d.status, nullptr, d.st));
+        SPE_TRY(launch_small(pdb, d.ps.gram_part, pdb.nblk, SMALL_EIGVECS, d.Msmall, d.evals, d.status, nullptr, d.st));
         SPE_TRY(launch_apply(pdb, d.buf[BQ], d.Msmall, d.buf[BV1], nullptr, nullptr, d.ps.ticket, d.st));   // Ritz vectors
         SPE_TRY(launch_apply(pdb, d.buf[BZ], d.Msmall, d.buf[BV2], nullptr, nullptr, d.ps.ticket, d.st));   // S * Ritz vectors
         SPE_TRY(launch_residual_norms(pdb, d.buf[BV2], d.buf[BV1], d.evals, d.ps, d.scal + 64, d.st));
@@ -723,7 +739,7 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
       for (Dev& d : devs) {
         SPE_CUDA(cudaSetDevice(d.ordinal));
         SPE_TRY(launch_gram(pdb, d.buf[BQ], d.buf[BZ], d.ps.gram_part, d.st));     // T = Q^H S Q
-        SPE_TRY(launch_small(pdb, d.ps.gram_part, kPanelBlocks, SMALL_EIGVECS, d.Msmall, d.evals, d.status, nullptr, d.st));
+        SPE_TRY(launch_small(pdb, d.ps.gram_part, pdb.nblk, SMALL_EIGVECS, d.Msmall, d.evals, d.status, nullptr, d.st));
         SPE_CUDA(cudaMemcpyAsync(d.scal, d.evals, bq * sizeof(double), cudaMemcpyDeviceToDevice, d.st));
         SPE_TRY(launch_axpby(pdb, d.buf[BQ], d.buf[BZ], sigma, -1.0, d.buf[BT1], d.st));   // (sigma I - S) Q
       }

@@ -75,6 +75,7 @@ class Solver {
   int64_t m = 0, n = 0;
   int q = 0;          // requested eigenvectors
   int bq = 0;         // initialiser block size (>= q)
+  int bq0 = 0;        // block size chosen at creation
   int64_t mrows = 0;  // allocated panel rows
   int64_t rows_per_shard = 0;
   PanelDims pdq, pdb;
@@ -90,6 +91,7 @@ class Solver {
 
   int create(const speigen_problem* p, const speigen_cfg* c);
   void destroy();
+  void reset_for_reuse();   // forget the previous problem's state, keep every allocation
   int init_comm_all();
   int init_comm_rank(const void* id128);
   int load_host(const double* X);

@@ -29,6 +29,16 @@ def test_library_exports_every_declared_symbol():
     assert L.speigen_abi_version() == 1
 
 
+def test_r_glue_uses_only_exported_symbols():
+    """integration/r-package/src/speigen_glue.c (the .Call stub of INTEGRATION.md) binds only exported ABI symbols."""
+    src = open(os.path.join(ROOT, "integration", "r-package", "src", "speigen_glue.c")).read()
+    used = set(re.findall(r"\b(speigen_(?:run_f64|run_c64|cfg_default|last_error|shutdown))\s*\(", src))
+    assert {"speigen_run_f64", "speigen_run_c64", "speigen_cfg_default", "speigen_last_error", "speigen_shutdown"} <= used
+    L = sb.lib()
+    for s in used:
+        assert hasattr(L, s)
+
+
 def test_validate_args_matches_reference_conditions():
     L = sb.lib()
     assert L.speigen_validate_args(15, 10, 3.0, 0.5) == 0
