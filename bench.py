@@ -49,7 +49,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -78,6 +78,25 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def ncu_traffic_bytes(m, q, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the contraction kernel from the committed ncu --set full
+    capture (profiles/r01_ncu_prof_contract_r01.csv), valid for the default single-GPU workload only; else None."""
+    if (m, q, world) != (50000, 20, 1):
+        return None
+    p = os.path.join(ROOT, "profiles", "r01_ncu_prof_contract_r01.csv")
+    try:
+        rd = wr = None
+        for line in open(p):
+            f = line.strip().split(",")
+            if f[0] == "dram__bytes_read.sum":
+                rd = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+            if f[0] == "dram__bytes_write.sum":
+                wr = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+        return rd + wr if rd is not None and wr is not None else None
+    except OSError:
+        return None
 
 
 def synth_cov_rows(m, n, q, card, lo, hi, device, seed=42):
@@ -274,7 +293,8 @@ def main():
                        "l2": "inputs larger than L2 (S shard = %.1f GB per GPU streamed every step)" % (8.0 * rows_local * m / 1e9),
                        "step": "one MM update = fused contraction+reweight, 2x(Gram, Jacobi, apply)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_contract_std<3>", "ms_per_launch": kern_ms,
+                         "traffic": ncu_traffic_bytes(m, q, world), "traffic_source": "profiles/r01_ncu_prof_contract_r01.csv (ncu --set full, one launch)",
+                         "kernel": "k_contract_std<3,0>", "ms_per_launch": kern_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "launches_timed": k_n},
             "gpu_launches": int(launches),
             "full_solve": {"seconds_loop": info["seconds_loop"], "seconds_total": solve_s, "outer_iterations": info["iterations"],

@@ -820,7 +820,7 @@ int launch_contract_std(const StreamMat& A, const double* P, int ncr, const EpiA
   prm.u_tile_bytes = static_cast<uint32_t>(kTK * prm.p_pitch * sizeof(double));
   prm.stage_bytes = kAStageBytes + round_up_u32(prm.u_tile_bytes + 512, 1024);
   prm.stages = static_cast<int>(kMaxDynSmem / prm.stage_bytes);
-  if (prm.stages > 4) prm.stages = 4;
+  if (prm.stages > 6) prm.stages = 6;
   if (prm.stages < 2) {
     set_error("contract: not enough shared memory for a 2-stage pipeline");
     return SPEIGEN_ERR_ARG;
@@ -894,7 +894,7 @@ int launch_contract_tr(const StreamMat& A, const double* P, int ncr, double* T, 
   prm.u_tile_bytes = static_cast<uint32_t>(kTrRows * prm.p_pitch * sizeof(double));
   prm.stage_bytes = kTrAStageBytes + round_up_u32(prm.u_tile_bytes + 512, 1024);
   prm.stages = static_cast<int>(kMaxDynSmem / prm.stage_bytes);
-  if (prm.stages > 4) prm.stages = 4;
+  if (prm.stages > 6) prm.stages = 6;
   if (prm.stages < 2) {
     set_error("contract_tr: not enough shared memory for a 2-stage pipeline");
     return SPEIGEN_ERR_ARG;
