@@ -135,28 +135,21 @@ int Solver::alloc_dev(Dev& d) {
     set_error("out of device memory allocating the %.2f GB matrix shard", a_bytes / 1e9);
     return SPEIGEN_ERR_NOMEM;
   }
+  // Everything except the matrix shard and the IPC-exported exchange buffers is carved out of ONE arena per device:
+  // ~45 cudaMalloc/cudaFree pairs per device cost more than the whole 8-GPU solve (0.35 s of a 0.53 s call).
   const size_t pbytes = static_cast<size_t>(mrows) * pdb.pitch * sizeof(double);
-  for (int b = 0; b < NBUF; ++b) {
-    SPE_CUDA(cudaMalloc(&d.buf[b], pbytes));
-    SPE_CUDA(cudaMemsetAsync(d.buf[b], 0, pbytes, d.st));
-  }
-  if (cplx && !data) {
-    SPE_CUDA(cudaMalloc(&d.hat, 2 * pbytes));
-    SPE_CUDA(cudaMemsetAsync(d.hat, 0, 2 * pbytes, d.st));
-  }
+  std::vector<std::pair<void**, size_t>> req;
+  auto want = [&](auto** p, size_t bytes) { req.emplace_back(reinterpret_cast<void**>(p), (bytes + 255) / 256 * 256); };
+  for (int bb = 0; bb < NBUF; ++bb) want(&d.buf[bb], pbytes);
+  if (cplx && !data) want(&d.hat, 2 * pbytes);
   if (data) {
-    const size_t tb = static_cast<size_t>(padded_rows(std::max<int64_t>(d.a_kd, 1))) * pdb.pitch * sizeof(double);
-    SPE_CUDA(cudaMalloc(&d.Tdata, tb));
-    SPE_CUDA(cudaMemsetAsync(d.Tdata, 0, tb, d.st));
-    if (prob.world > 1) {
-      SPE_CUDA(cudaMalloc(&d.gather, pbytes * prob.world));
-      SPE_CUDA(cudaMemsetAsync(d.gather, 0, pbytes * prob.world, d.st));
-    }
+    want(&d.Tdata, static_cast<size_t>(padded_rows(std::max<int64_t>(d.a_kd, 1))) * pdb.pitch * sizeof(double));
+    if (prob.world > 1) want(&d.gather, pbytes * prob.world);
   }
   // contraction workspace (both forms share it; sized for the larger)
   const int ncr_max = bq * e;
   size_t slots = contract_workspace_slots(d.a_rows, d.num_sms);
-  size_t slot_d = contract_slot_doubles(ncr_max);
+  const size_t slot_d = contract_slot_doubles(ncr_max);
   int ncount = static_cast<int>((d.a_rows + kTJ - 1) / kTJ);
   if (data) {
     slots = std::max(slots, contract_tr_workspace_slots(d.a_kd, d.num_sms));
@@ -164,29 +157,41 @@ int Solver::alloc_dev(Dev& d) {
   }
   d.ws.partial_slots = slots;
   d.ws.n_counters = ncount + 1;
-  SPE_CUDA(cudaMalloc(&d.ws.partials, slots * slot_d * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.ws.counters, d.ws.n_counters * sizeof(int)));
-  SPE_CUDA(cudaMemsetAsync(d.ws.counters, 0, d.ws.n_counters * sizeof(int), d.st));
+  want(&d.ws.partials, slots * slot_d * sizeof(double));
+  want(&d.ws.counters, d.ws.n_counters * sizeof(int));
   const size_t glen = static_cast<size_t>(bq * e) * (bq * e);   // real Gram / real hat form of the small matrix
-  SPE_CUDA(cudaMalloc(&d.ps.gram_part, kPanelBlocks * glen * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.gram_part2, kPanelBlocks * glen * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.ps.col_part, kPanelBlocks * 2 * kMaxCols * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.ps.ticket, sizeof(int)));
-  SPE_CUDA(cudaMemsetAsync(d.ps.ticket, 0, sizeof(int), d.st));
-  SPE_CUDA(cudaMalloc(&d.absmin_a, (kPanelBlocks + 1) * kMaxCols * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.absmin_b, (kPanelBlocks + 1) * kMaxCols * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.Msmall, glen * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.evals, kMaxCols * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.warm, 4 * kWarmStride * sizeof(double)));
-  SPE_CUDA(cudaMemsetAsync(d.warm, 0, 4 * kWarmStride * sizeof(double), d.st));
-  SPE_CUDA(cudaMalloc(&d.status, sizeof(int)));
-  SPE_CUDA(cudaMemsetAsync(d.status, 0, sizeof(int), d.st));
-  SPE_CUDA(cudaMalloc(&d.dvec, kMaxCols * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.rho, kMaxCols * sizeof(double)));
+  want(&d.ps.gram_part, kPanelBlocks * glen * sizeof(double));
+  want(&d.gram_part2, kPanelBlocks * glen * sizeof(double));
+  want(&d.ps.col_part, kPanelBlocks * 2 * kMaxCols * sizeof(double));
+  want(&d.ps.ticket, sizeof(int));
+  want(&d.absmin_a, (kPanelBlocks + 1) * kMaxCols * sizeof(double));
+  want(&d.absmin_b, (kPanelBlocks + 1) * kMaxCols * sizeof(double));
+  want(&d.Msmall, glen * sizeof(double));
+  want(&d.evals, kMaxCols * sizeof(double));
+  want(&d.warm, 4 * kWarmStride * sizeof(double));
+  want(&d.status, sizeof(int));
+  want(&d.dvec, kMaxCols * sizeof(double));
+  want(&d.rho, kMaxCols * sizeof(double));
   const size_t ntiles = static_cast<size_t>((d.a_rows + kTJ - 1) / kTJ) + 1;
-  SPE_CUDA(cudaMalloc(&d.dots_part, std::max<size_t>(ntiles, kPanelBlocks) * kMaxCols * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.dots_gather, static_cast<size_t>(prob.world) * kMaxCols * sizeof(double)));
-  if (!data && prob.world > 1 && prob.world <= kMaxPeers) {
+  want(&d.dots_part, std::max<size_t>(ntiles, kPanelBlocks) * kMaxCols * sizeof(double));
+  want(&d.dots_gather, static_cast<size_t>(prob.world) * kMaxCols * sizeof(double));
+  want(&d.done_count, sizeof(int));
+  want(&d.scal, 512 * sizeof(double));
+  want(&d.vecm, static_cast<size_t>(2 * m + 16) * sizeof(double));
+  want(&d.vecm2, static_cast<size_t>(2 * m + 16) * sizeof(double));
+  want(&d.scan_part, kScanBlocks * 4 * sizeof(double));
+  want(&d.out_cm, static_cast<size_t>(m) * bq * e * sizeof(double));
+  size_t total = 0;
+  for (auto& r : req) total += r.second;
+  if (cudaMalloc(&d.arena, total) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("out of device memory allocating %.2f GB of panel workspace", total / 1e9);
+    return SPEIGEN_ERR_NOMEM;
+  }
+  SPE_CUDA(cudaMemsetAsync(d.arena, 0, total, d.st));
+  size_t off = 0;
+  for (auto& r : req) { *r.first = static_cast<char*>(d.arena) + off; off += r.second; }
+  if (!data && prob.world > 1 && prob.world <= kMaxPeers) {   // separate allocations: exported with cudaIpcGetMemHandle
     const size_t xb_bytes = 4 * pbytes;
     SPE_CUDA(cudaMalloc(&d.xb, xb_bytes));
     SPE_CUDA(cudaMemsetAsync(d.xb, 0, xb_bytes, d.st));
@@ -194,15 +199,7 @@ int Solver::alloc_dev(Dev& d) {
     SPE_CUDA(cudaMemsetAsync(d.xdots, 0, 2 * static_cast<size_t>(prob.world) * kMaxCols * sizeof(double), d.st));
     SPE_CUDA(cudaMalloc(&d.xflags, kMaxPeers * sizeof(unsigned long long)));
     SPE_CUDA(cudaMemsetAsync(d.xflags, 0, kMaxPeers * sizeof(unsigned long long), d.st));
-    SPE_CUDA(cudaMalloc(&d.done_count, sizeof(int)));
-    SPE_CUDA(cudaMemsetAsync(d.done_count, 0, sizeof(int), d.st));
   }
-  SPE_CUDA(cudaMalloc(&d.scal, 512 * sizeof(double)));
-  SPE_CUDA(cudaMemsetAsync(d.scal, 0, 512 * sizeof(double), d.st));
-  SPE_CUDA(cudaMalloc(&d.vecm, static_cast<size_t>(2 * m + 16) * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.vecm2, static_cast<size_t>(2 * m + 16) * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.scan_part, kScanBlocks * 4 * sizeof(double)));
-  SPE_CUDA(cudaMalloc(&d.out_cm, static_cast<size_t>(m) * bq * e * sizeof(double)));
   SPE_CUDA(cudaStreamSynchronize(d.st));
   return SPEIGEN_OK;
 }
@@ -213,13 +210,9 @@ void Solver::destroy() {
     if (d.st) cudaStreamSynchronize(d.st);
     for (int i = 0; i < d.n_ipc_opened; ++i) cudaIpcCloseMemHandle(d.ipc_opened[i]);
     if (d.comm && nccl_api()) nccl_api()->CommDestroy(d.comm);
-    void* ptrs[] = {d.A, d.hat, d.Tdata, d.gather, d.ws.partials, d.ws.counters, d.ps.gram_part, d.gram_part2,
-                    d.ps.col_part, d.ps.ticket, d.absmin_a, d.absmin_b, d.Msmall, d.evals, d.warm, d.status, d.dvec, d.rho,
-                    d.dots_part, d.dots_gather, d.scal, d.vecm, d.vecm2, d.scan_part, d.out_cm, d.flush, d.xb, d.xdots, d.xflags, d.done_count};
+    void* ptrs[] = {d.A, d.arena, d.xb, d.xdots, d.xflags, d.flush};
     for (void* p : ptrs)
       if (p) cudaFree(p);
-    for (int b = 0; b < NBUF; ++b)
-      if (d.buf[b]) cudaFree(d.buf[b]);
     if (d.st) cudaStreamDestroy(d.st);
   }
   devs.clear();
@@ -248,6 +241,10 @@ int Solver::init_comm_all() {
     set_error("single-process communicator needs all %d shards local (have %zu)", prob.world, devs.size());
     return SPEIGEN_ERR_ARG;
   }
+  // Row-sharded covariance inside one process: the fused peer-store exchange needs no NCCL communicator at all
+  // (ncclCommInitAll costs hundreds of milliseconds, more than the whole solve at m = 50k on 8 GPUs).
+  SPE_TRY(init_p2p());
+  if (p2p && !data) { comm_ready = true; return SPEIGEN_OK; }
   const NcclApi* nc = nccl_api();
   if (!nc) return SPEIGEN_ERR_NCCL;
   std::vector<int> ords;
@@ -402,8 +399,9 @@ int Solver::build_tensor_maps() {
 
 // ---- validation scan, centring, rho scale -------------------------------------------------------
 int Solver::prepare() {
-  const NcclApi* nc = prob.world > 1 ? nccl_api() : nullptr;
-  if (prob.world > 1 && (!nc || !comm_ready)) {
+  const bool need_nccl = prob.world > 1 && (data || !p2p || devs[0].comm != nullptr);
+  const NcclApi* nc = need_nccl ? nccl_api() : nullptr;
+  if (prob.world > 1 && ((need_nccl && !nc) || !comm_ready)) {
     set_error("multi-GPU solver used before the communicator was initialised");
     return SPEIGEN_ERR_NCCL;
   }
@@ -414,7 +412,7 @@ int Solver::prepare() {
       SPE_CUDA(cudaSetDevice(d.ordinal));
       SPE_TRY(launch_scan_cov(d.A, d.a_rows, m, d.a_ld, d.lo, cplx, full, d.scan_part, d.ps.ticket, d.scal, d.st));
     }
-    if (prob.world > 1) {
+    if (prob.world > 1 && devs[0].comm) {
       SPE_NCCL(nc->GroupStart());
       for (Dev& d : devs) {
         SPE_NCCL(nc->AllReduce(d.scal + 2, d.scal + 2, 1, NCCL_DOUBLE, NCCL_MAX, d.comm, d.st));
@@ -423,6 +421,19 @@ int Solver::prepare() {
       SPE_NCCL(nc->GroupEnd());
     }
     SPE_TRY(read_scalars(4));
+    if (prob.world > 1 && !devs[0].comm) {   // single process without a communicator: combine the shards on the host
+      double mx = h_scal[2], nn = h_scal[3];
+      for (size_t i = 1; i < devs.size(); ++i) {
+        double tmp[4];
+        SPE_CUDA(cudaSetDevice(devs[i].ordinal));
+        SPE_CUDA(cudaMemcpyAsync(tmp, devs[i].scal, sizeof(tmp), cudaMemcpyDeviceToHost, devs[i].st));
+        SPE_CUDA(cudaStreamSynchronize(devs[i].st));
+        mx = std::max(mx, tmp[2]);
+        nn += tmp[3];
+      }
+      h_scal[2] = mx;
+      h_scal[3] = nn;
+    }
     if (cfg.check_na && (h_scal[3] > 0.0 || std::isnan(h_scal[1]))) {
       set_error("This function cannot handle NAs.");
       return SPEIGEN_ERR_NA;

@@ -24,6 +24,7 @@ struct Dev {
   int num_sms = 148;
   // streamed matrix shard
   double* A = nullptr;
+  void* arena = nullptr;       // one allocation backing every panel / scratch buffer below
   int64_t a_rows = 0, a_kd = 0, a_ld = 0;   // rows, contiguous doubles, pitch
   int64_t lo = 0, hi = 0;                   // owned global range (rows of S / samples of X)
   StreamMat Astd, Atr;
