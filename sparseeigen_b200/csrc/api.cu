@@ -19,6 +19,13 @@ using namespace speigen;
     if (rc__ != SPEIGEN_OK) return rc__; \
   } while (0)
 
+// Every entry point leaves the caller's current CUDA device as it found it (a host such as PyTorch caches it).
+struct DeviceRestore {
+  int prev = -1;
+  DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+  ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static double wall_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -114,6 +121,7 @@ int64_t speigen_matrix_ld(int64_t contiguous_doubles) { return (contiguous_doubl
 
 // ---- resident solver --------------------------------------------------------------------------
 int speigen_solver_create(speigen_solver** s, const speigen_problem* prob, const speigen_cfg* cfg) {
+  DeviceRestore restore_device__;
   if (!s || !prob) return SPEIGEN_ERR_ARG;
   speigen_cfg def;
   if (!cfg) { speigen_cfg_default(&def); cfg = &def; }
@@ -125,6 +133,7 @@ int speigen_solver_create(speigen_solver** s, const speigen_problem* prob, const
   return SPEIGEN_OK;
 }
 int speigen_solver_destroy(speigen_solver* s) {
+  DeviceRestore restore_device__;
   if (!s) return SPEIGEN_OK;
   s->impl.destroy();
   delete s;
@@ -140,12 +149,15 @@ int speigen_nccl_unique_id(void* id128) {
   return SPEIGEN_OK;
 }
 int speigen_solver_init_comm(speigen_solver* s, const void* id128) {
+  DeviceRestore restore_device__;
   if (!s) return SPEIGEN_ERR_ARG;
   return id128 ? s->impl.init_comm_rank(id128) : s->impl.init_comm_all();
 }
-int speigen_solver_load_host(speigen_solver* s, const double* X) { return s->impl.load_host(X); }
+int speigen_solver_load_host(speigen_solver* s, const double* X) {
+  DeviceRestore restore_device__; return s->impl.load_host(X); }
 int speigen_solver_shard_buffer(speigen_solver* s, int32_t li, double** dev_ptr, int64_t* rows, int64_t* row_len,
                                 int64_t* ld, int64_t* lo, int64_t* hi) {
+  DeviceRestore restore_device__;
   if (!s || li < 0 || li >= static_cast<int>(s->impl.devs.size())) return SPEIGEN_ERR_ARG;
   Dev& d = s->impl.devs[li];
   if (dev_ptr) *dev_ptr = d.A;
@@ -157,15 +169,20 @@ int speigen_solver_shard_buffer(speigen_solver* s, int32_t li, double** dev_ptr,
   s->impl.loaded = true;
   return SPEIGEN_OK;
 }
-int speigen_solver_prepare(speigen_solver* s) { return s->impl.prepare(); }
-int speigen_solver_init(speigen_solver* s, const double* V0, speigen_out* out) { return s->impl.init_vectors(V0, out); }
+int speigen_solver_prepare(speigen_solver* s) {
+  DeviceRestore restore_device__; return s->impl.prepare(); }
+int speigen_solver_init(speigen_solver* s, const double* V0, speigen_out* out) {
+  DeviceRestore restore_device__; return s->impl.init_vectors(V0, out); }
 int speigen_solver_run(speigen_solver* s, double rho, const double* d, double thres, speigen_out* out) {
+  DeviceRestore restore_device__;
   if (std::isnan(rho)) { set_error("This function cannot handle NAs."); return SPEIGEN_ERR_NA; }
   if (rho <= 0) { set_error("The input argument rho should be positive."); return SPEIGEN_ERR_RHO; }
   return s->impl.run(rho, d, thres, out);
 }
-int64_t speigen_solver_launch_count(speigen_solver*) { return launch_count(); }
+int64_t speigen_solver_launch_count(speigen_solver*) {
+  DeviceRestore restore_device__; return launch_count(); }
 int speigen_solver_stream(speigen_solver* s, int32_t li, void** st) {
+  DeviceRestore restore_device__;
   if (!s || li < 0 || li >= static_cast<int>(s->impl.devs.size())) return SPEIGEN_ERR_ARG;
   *st = s->impl.devs[li].st;
   return SPEIGEN_OK;
@@ -178,6 +195,7 @@ static int ensure_maps(Solver& S) {
 }
 
 int speigen_solver_contract(speigen_solver* s, const double* U_host, int32_t ncols, double* Y_host) {
+  DeviceRestore restore_device__;
   Solver& S = s->impl;
   if (ncols < 1 || ncols > S.bq) { set_error("contract: ncols %d outside 1..%d", ncols, S.bq); return SPEIGEN_ERR_ARG; }
   API_TRY(ensure_maps(S));
@@ -188,6 +206,7 @@ int speigen_solver_contract(speigen_solver* s, const double* U_host, int32_t nco
 }
 
 int speigen_solver_polar(speigen_solver* s, const double* A_host, int32_t ncols, double* U_host) {
+  DeviceRestore restore_device__;
   Solver& S = s->impl;
   if (ncols < 1 || ncols > S.bq) { set_error("polar: ncols %d outside 1..%d", ncols, S.bq); return SPEIGEN_ERR_ARG; }
   const PanelDims pd = make_dims(S.m, ncols, S.cplx);
@@ -198,6 +217,7 @@ int speigen_solver_polar(speigen_solver* s, const double* A_host, int32_t ncols,
 
 int speigen_solver_mm_update(speigen_solver* s, const double* V_host, const double* d, const double* rho_vec, double p,
                              double eps, int32_t fused, double* V1_host) {
+  DeviceRestore restore_device__;
   Solver& S = s->impl;
   API_TRY(ensure_maps(S));
   const PanelDims pd = S.pdq;
@@ -225,6 +245,7 @@ int speigen_solver_mm_update(speigen_solver* s, const double* V_host, const doub
 
 int speigen_solver_objective(speigen_solver* s, const double* V_host, const double* d, const double* rho_vec, double p,
                              double eps, double* F_out) {
+  DeviceRestore restore_device__;
   Solver& S = s->impl;
   API_TRY(ensure_maps(S));
   const PanelDims pd = S.pdq;
@@ -242,6 +263,7 @@ int speigen_solver_objective(speigen_solver* s, const double* V_host, const doub
 }
 
 int speigen_solver_eig_small(speigen_solver* s, const double* C_host, int32_t nn, double* W_host, double* evals) {
+  DeviceRestore restore_device__;
   Solver& S = s->impl;
   if (nn < 1 || nn > S.bq) { set_error("eig_small: n %d outside 1..%d", nn, S.bq); return SPEIGEN_ERR_ARG; }
   const int e = 1 + S.cplx;
@@ -280,24 +302,32 @@ int speigen_solver_eig_small(speigen_solver* s, const double* C_host, int32_t nn
 }
 
 int speigen_solver_time_contract(speigen_solver* s, int32_t ncols, int32_t reps, int32_t flush_l2, float* ms_each) {
+  DeviceRestore restore_device__;
   Solver& S = s->impl;
   API_TRY(ensure_maps(S));
   return S.time_contract(ncols, reps, flush_l2, ms_each);
 }
 
 int speigen_solver_load_device(speigen_solver* s, int32_t li, const double* dev_src, int64_t src_ld) {
+  DeviceRestore restore_device__;
   return s->impl.load_device(li, dev_src, src_ld);
 }
 int speigen_solver_load_device_rows(speigen_solver* s, int32_t li, int64_t row0, int64_t nrows, const double* dev_src, int64_t src_ld) {
+  DeviceRestore restore_device__;
   return s->impl.load_device_rows(li, row0, nrows, dev_src, src_ld);
 }
 int speigen_solver_mm_steps(speigen_solver* s, int32_t nsteps, int32_t stage, double rho, const double* d, float* ms_out) {
+  DeviceRestore restore_device__;
   return s->impl.mm_steps(nsteps, stage, rho, d, ms_out);
 }
-int speigen_solver_sync(speigen_solver* s) { return s->impl.sync_all(); }
-int speigen_solver_exchange_mode(speigen_solver* s) { return s->impl.prob.world <= 1 ? 0 : (s->impl.p2p ? 2 : 1); }
-int speigen_solver_kernel_timing(speigen_solver* s, int32_t enable) { s->impl.enable_kernel_timing(enable != 0); return SPEIGEN_OK; }
+int speigen_solver_sync(speigen_solver* s) {
+  DeviceRestore restore_device__; return s->impl.sync_all(); }
+int speigen_solver_exchange_mode(speigen_solver* s) {
+  DeviceRestore restore_device__; return s->impl.prob.world <= 1 ? 0 : (s->impl.p2p ? 2 : 1); }
+int speigen_solver_kernel_timing(speigen_solver* s, int32_t enable) {
+  DeviceRestore restore_device__; s->impl.enable_kernel_timing(enable != 0); return SPEIGEN_OK; }
 int speigen_solver_kernel_time(speigen_solver* s, double* ms_total, int32_t* launches) {
+  DeviceRestore restore_device__;
   int n = 0;
   const int rc = s->impl.kernel_time(ms_total, &n);
   *launches = n;
@@ -310,12 +340,14 @@ static speigen_problem g_cached_prob;
 static speigen_cfg g_cached_cfg;
 
 int speigen_shutdown(void) {
+  DeviceRestore restore_device__;
   if (g_cached) { speigen_solver_destroy(g_cached); g_cached = nullptr; }
   return SPEIGEN_OK;
 }
 
 static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data, int is_complex, double q, double rho,
                        const double* d, const double* V0, double thres, const speigen_cfg* cfg_in, speigen_out* out) {
+  DeviceRestore restore_device__;
   if (!X || !out) { set_error("null argument"); return SPEIGEN_ERR_ARG; }
   speigen_cfg cfg;
   if (cfg_in) cfg = *cfg_in; else speigen_cfg_default(&cfg);

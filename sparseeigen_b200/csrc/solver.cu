@@ -870,7 +870,9 @@ int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) 
       }
       SPE_TRY(read_scalars(2));
       const double nR = h_scal[0], nU = h_scal[1];
-      double a = std::min(-nR / nU, -1.0);     // nU == 0 -> -Inf as in R; NaN (0/0) -> -1
+      // a <- min(-||R||/||U||, -1)   :123.  ||U|| == 0 (V2 - 2 V1 + V vanished exactly) gives -Inf in R and then a NaN
+      // iterate that makes svd() fail; here that case takes the plain double MM step a = -1 (V0 = V2) instead.
+      double a = (nU > 0.0) ? std::min(-nR / nU, -1.0) : -1.0;
       if (a != a) a = -1.0;
       int nbt = 0;
       double Fk = 0.0;

@@ -245,6 +245,25 @@ def test_run_is_bit_reproducible():
     assert np.array_equal(a["vectors"], b["vectors"]) and np.array_equal(a["info"]["F"], b["info"]["F"])
 
 
+def test_cached_context_carries_no_state_between_calls():
+    """The one-shot call keeps a small solver alive between calls of the same shape; results must not depend on it."""
+    Xa, _ = o.spiked_samples(600, 150, 4, 0.05, seed=31)
+    Xb, _ = o.spiked_samples(600, 150, 4, 0.05, seed=32)
+    Sa, Sb = o.sample_cov(Xa), o.sample_cov(Xb)
+    sb.lib().speigen_shutdown()
+    a1 = sb.spEigen(Sa, 4)                 # fresh context
+    b1 = sb.spEigen(Sb, 4)                 # reused context, different data
+    a2 = sb.spEigen(Sa, 4)                 # reused again
+    low = Xa[:3].T @ Xa[:3]
+    with pytest.raises(sb.SpEigenError, match="rank"): sb.spEigen(low, 4)     # error path on a reused context
+    a3 = sb.spEigen(Sa, 4)
+    sb.lib().speigen_shutdown()
+    b2 = sb.spEigen(Sb, 4)                 # fresh context again
+    for r in (a2, a3):
+        assert np.array_equal(a1["vectors"], r["vectors"]) and np.array_equal(a1["info"]["F"], r["info"]["F"])
+    assert np.array_equal(b1["vectors"], b2["vectors"]) and np.array_equal(b1["values"], b2["values"])
+
+
 # ---------------------------------------------------------------------------------------------------
 # the reference's behavioural tests at the boundary (tests/testthat/test-sparseEigen.R)
 # ---------------------------------------------------------------------------------------------------
