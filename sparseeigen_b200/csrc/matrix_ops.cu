@@ -20,9 +20,15 @@ __device__ __forceinline__ double warp_max_d(double v) {
 }
 
 // 32 x 32 element tiles, 32 x 8 threads.  E = doubles per element.
+struct ScanPeers {
+  const double* A[8];   // shard base pointers of every row block (as mapped into this device); [0] = own for 1 GPU
+  int64_t rps;          // rows per shard
+};
+
 template <int E>
 __global__ void __launch_bounds__(256) k_scan_cov(const double* A, int64_t rows, int64_t m, int64_t ld, int64_t lo,
-                                                  int full_check, double* part, int* ticket, double* out4) {
+                                                  int full_check, const ScanPeers peers, double* part, int* ticket,
+                                                  double* out4) {
   __shared__ double tileT[32][32 * E + 1];
   __shared__ double s_red[4][8];
   __shared__ int s_is_last;
@@ -33,11 +39,13 @@ __global__ void __launch_bounds__(256) k_scan_cov(const double* A, int64_t rows,
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t tj = t / tc, ti = t - tj * tc;
     if (full_check) {
-      // transposed tile: rows ti*32.., columns tj*32..
+      // transposed tile: global rows ti*32.. (owned by shard g/rps), global columns lo + tj*32..
       for (int r = ty; r < 32; r += 8) {
-        const int64_t jj = ti * 32 + r, ii = tj * 32 + tx;
+        const int64_t gg = ti * 32 + r, ii = lo + tj * 32 + tx;
+        const bool ok = gg < m && (tj * 32 + tx) < rows;
+        const double* src = ok ? peers.A[gg / peers.rps] + (gg % peers.rps) * ld + ii * E : nullptr;
 #pragma unroll
-        for (int e = 0; e < E; ++e) tileT[r][tx * E + e] = (jj < rows && ii < m) ? A[jj * ld + ii * E + e] : 0.0;
+        for (int e = 0; e < E; ++e) tileT[r][tx * E + e] = ok ? src[e] : 0.0;
       }
       __syncthreads();
     }
@@ -152,9 +160,13 @@ __global__ void __launch_bounds__(256) k_vec_max(const double* v, int64_t n, dou
 }  // namespace
 
 int launch_scan_cov(const double* A, int64_t rows, int64_t m, int64_t ld, int64_t lo, int cplx, int full_check,
-                    double* part, int* ticket, double* out4, cudaStream_t st) {
-  if (cplx) k_scan_cov<2><<<kScanBlocks, 256, 0, st>>>(A, rows, m, ld, lo, full_check, part, ticket, out4);
-  else k_scan_cov<1><<<kScanBlocks, 256, 0, st>>>(A, rows, m, ld, lo, full_check, part, ticket, out4);
+                    const double* const* shard_ptrs, int nshards, int64_t rows_per_shard, double* part, int* ticket,
+                    double* out4, cudaStream_t st) {
+  ScanPeers peers{};
+  for (int i = 0; i < 8; ++i) peers.A[i] = (shard_ptrs && i < nshards) ? shard_ptrs[i] : A;
+  peers.rps = (shard_ptrs && nshards > 1) ? rows_per_shard : (m > 0 ? m : 1);
+  if (cplx) k_scan_cov<2><<<kScanBlocks, 256, 0, st>>>(A, rows, m, ld, lo, full_check, peers, part, ticket, out4);
+  else k_scan_cov<1><<<kScanBlocks, 256, 0, st>>>(A, rows, m, ld, lo, full_check, peers, part, ticket, out4);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

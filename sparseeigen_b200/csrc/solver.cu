@@ -407,10 +407,17 @@ int Solver::prepare() {
   }
   SPE_TRY(build_tensor_maps());
   if (!data) {
-    const int full = (prob.world == 1 && (cfg.check_symmetric || cfg.check_na)) ? 1 : 0;
+    // isSymmetric.matrix needs S[i,j] next to S[j,i]: possible on one GPU, and on several GPUs of ONE process when peer
+    // access is up (the transposed tile is read from the shard that owns it); one-process-per-GPU runs trust the caller.
+    const bool single_process = static_cast<int>(devs.size()) == prob.world;
+    const bool can_check = prob.world == 1 || (single_process && p2p);
+    const int full = (can_check && (cfg.check_symmetric || cfg.check_na)) ? 1 : 0;
+    std::vector<const double*> shard_ptrs(prob.world, nullptr);
+    if (single_process) for (Dev& d : devs) shard_ptrs[d.shard] = d.A;
     for (Dev& d : devs) {
       SPE_CUDA(cudaSetDevice(d.ordinal));
-      SPE_TRY(launch_scan_cov(d.A, d.a_rows, m, d.a_ld, d.lo, cplx, full, d.scan_part, d.ps.ticket, d.scal, d.st));
+      SPE_TRY(launch_scan_cov(d.A, d.a_rows, m, d.a_ld, d.lo, cplx, full, prob.world > 1 ? shard_ptrs.data() : nullptr,
+                              prob.world, rows_per_shard, d.scan_part, d.ps.ticket, d.scal, d.st));
     }
     if (prob.world > 1 && devs[0].comm) {
       SPE_NCCL(nc->GroupStart());
@@ -421,16 +428,19 @@ int Solver::prepare() {
       SPE_NCCL(nc->GroupEnd());
     }
     SPE_TRY(read_scalars(4));
-    if (prob.world > 1 && !devs[0].comm) {   // single process without a communicator: combine the shards on the host
-      double mx = h_scal[2], nn = h_scal[3];
+    if (prob.world > 1 && single_process) {   // combine the shards' sums on the host (fixed device order)
+      double df = h_scal[0], sa = h_scal[1], mx = h_scal[2], nn = h_scal[3];
       for (size_t i = 1; i < devs.size(); ++i) {
         double tmp[4];
         SPE_CUDA(cudaSetDevice(devs[i].ordinal));
         SPE_CUDA(cudaMemcpyAsync(tmp, devs[i].scal, sizeof(tmp), cudaMemcpyDeviceToHost, devs[i].st));
         SPE_CUDA(cudaStreamSynchronize(devs[i].st));
-        mx = std::max(mx, tmp[2]);
-        nn += tmp[3];
+        df += tmp[0];
+        sa += tmp[1];
+        if (!devs[0].comm) { mx = std::max(mx, tmp[2]); nn += tmp[3]; }
       }
+      h_scal[0] = df;
+      h_scal[1] = sa;
       h_scal[2] = mx;
       h_scal[3] = nn;
     }

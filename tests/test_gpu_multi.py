@@ -68,3 +68,21 @@ def test_e2e_two_gpus_matches_one():
     assert np.array_equal(c["vectors"] != 0, d["vectors"] != 0)
     assert np.all(colwise_inner(c["vectors"], d["vectors"]) > 1 - 1e-5)
     assert np.allclose(c["values"], d["values"], rtol=1e-12)
+
+
+@need2
+def test_sharded_validation_scan():
+    """isSymmetric.matrix / anyNA (R/spEigen.R:53,75) on a row-sharded covariance: the transposed entries live on the peer."""
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((300, 500))
+    S = np.cov(X, rowvar=False)
+    A = S.copy(); A[400, 7] += 1e-3                       # asymmetry across the two shards
+    with pytest.raises(sb.SpEigenError, match="not symmetric"): sb.spEigen(A, 3, n_gpus=2)
+    r = sb.spEigen(S, 3, n_gpus=2)
+    assert r["vectors"].shape == (500, 3)
+    import ctypes as C
+    Sn = np.asfortranarray(S.copy()); Sn[450, 450] = np.nan
+    ob = sb._OutBuffers(500, 3, False)
+    cfg = sb.default_cfg(n_gpus=2)
+    rc = sb.lib().speigen_run_f64(Sn.ctypes.data_as(sb._dp), 500, 500, 0, 3.0, 0.5, None, None, 1e-9, C.byref(cfg), C.byref(ob.c))
+    assert rc == 2
