@@ -575,6 +575,24 @@ __global__ void k_axpby(const double* X, const double* Y, double alpha, double b
   Out[g] = alpha * X[g] + beta * Y[g];
 }
 
+// Out = a * X + b * Y + c * Z on the valid m x ncr region (Chebyshev three-term recurrence)
+__global__ void k_axpbypcz(const double* X, const double* Y, const double* Z, double a, double b, double c, int64_t m,
+                           int ncr, int pitch, double* Out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= m * ncr) return;
+  const int64_t r = idx / ncr;
+  const size_t g = static_cast<size_t>(r) * pitch + (idx - r * ncr);
+  Out[g] = a * X[g] + b * Y[g] + c * Z[g];
+}
+// P[:, col] *= scale[col]  (scale per logical column; complex columns scale both parts)
+__global__ void k_scale_columns(double* P, const double* scale, int64_t m, int ncr, int e, int pitch) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= m * ncr) return;
+  const int64_t r = idx / ncr;
+  const int c = static_cast<int>(idx - r * ncr);
+  P[static_cast<size_t>(r) * pitch + c] *= scale[c / e];
+}
+
 __global__ void k_take_columns(const double* In, int64_t m, int ncr_out, int pitch_in, int pitch_out, double* Out) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= m * ncr_out) return;
@@ -1180,6 +1198,19 @@ int launch_residual_norms(const PanelDims& pd, const double* ZW, const double* Q
 }
 int launch_axpby(const PanelDims& pd, const double* X, const double* Y, double alpha, double beta, double* Out, cudaStream_t st) {
   k_axpby<<<nblk(pd.m * pd.ncr), 256, 0, st>>>(X, Y, alpha, beta, pd.m, pd.ncr, pd.pitch, Out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_axpbypcz(const PanelDims& pd, const double* X, const double* Y, const double* Z, double a, double b, double c,
+                    double* Out, cudaStream_t st) {
+  k_axpbypcz<<<nblk(pd.m * pd.ncr), 256, 0, st>>>(X, Y, Z, a, b, c, pd.m, pd.ncr, pd.pitch, Out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_scale_columns(const PanelDims& pd, double* P, const double* scale, cudaStream_t st) {
+  k_scale_columns<<<nblk(pd.m * pd.ncr), 256, 0, st>>>(P, scale, pd.m, pd.ncr, pd.cplx ? 2 : 1, pd.pitch);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

@@ -80,6 +80,9 @@ int launch_residual_norms(const PanelDims& pd, const double* ZW, const double* Q
                           const PanelScratch& sc, double* out, cudaStream_t st);
 // out[c] = max_j Re(diag) helper etc. live in the driver.
 int launch_axpby(const PanelDims& pd, const double* X, const double* Y, double alpha, double beta, double* Out, cudaStream_t st);
+int launch_axpbypcz(const PanelDims& pd, const double* X, const double* Y, const double* Z, double a, double b, double c,
+                    double* Out, cudaStream_t st);
+int launch_scale_columns(const PanelDims& pd, double* P, const double* scale, cudaStream_t st);
 // copy the first q_out logical columns of a (wider) panel into a q_out-column panel
 int launch_take_columns(const PanelDims& pd_in, const double* In, const PanelDims& pd_out, double* Out, cudaStream_t st);
 // fixed-order sum of nparts partial panels (data mode, multi-GPU): Out = sum_r In[r]

@@ -700,6 +700,8 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
     double prev = 1e300;
     int stall = 0;
     bool rank_bad = false;
+    int cheb_deg = 1;
+    double lam_low = 0.0;
     sv2.assign(bq, 0.0);
     for (passes = 1; passes <= cfg.init_max_passes; ++passes) {
       SPE_TRY(op_contract(BQ, pdb, BZ, NBUF, NBUF, false, sc0));
@@ -724,8 +726,50 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
       // round-off floor: residual stopped improving at a tiny level
       if (resid_rel > 0.5 * prev) ++stall; else stall = 0;
       if (stall >= 3 && resid_rel <= 1e-11) { converged = true; break; }
+      // Chebyshev acceleration for slowly separating spectra: when plain power steps gain less than 2x per pass, the
+      // Ritz vectors X are filtered with T_deg((S - c)/e), [c - e, c + e] = [lower bound, smallest Ritz value of the
+      // block] (the unwanted interval), each column rescaled by 1 / T_deg(x_c) so the block stays well conditioned.
+      // The degree doubles while convergence stays slow, capped so that wanted directions differ by <= 1e6 in gain.
+      const double rate = (prev < 1e299) ? resid_rel / prev : 0.0;
       prev = std::min(prev, resid_rel);
-      SPE_TRY(op_polar(BV2, BQ, pdb, false, nullptr, 0, WARM_INIT));
+      lam_low = std::min(lam_low, sv2[bq - 1]);
+      if (passes >= 3 && rate > 0.5 && bq > q) cheb_deg = std::min(cheb_deg * 2, 24);
+      int deg = cheb_deg;
+      const double ub = sv2[bq - 1], lb = std::min(0.0, lam_low);
+      const double cc = 0.5 * (ub + lb), ee = 0.5 * (ub - lb);
+      auto cheb = [](int d, double x) { return x > 1.0 ? std::cosh(d * std::acosh(x)) : 1.0; };
+      if (!(ub > 0.0)) deg = 1;   // the filter interval [lb, ub] assumes a PSD spectrum below the block
+      if (deg > 1) {
+        const double x0 = (sv2[0] - cc) / ee, xq = (sv2[q - 1] - cc) / ee;
+        while (deg > 1 && !(cheb(deg, x0) <= 1e6 * cheb(deg, xq))) --deg;   // also steps down on overflow (inf/NaN)
+      }
+      if (deg <= 1 || !(ee > 0.0)) {
+        SPE_TRY(op_polar(BV2, BQ, pdb, false, nullptr, 0, WARM_INIT));
+      } else {
+        Buf yprev = BV1, ycur = BT1, yspare = BV0;
+        for (Dev& d : devs) {   // Y1 = (S X - c X) / e
+          SPE_CUDA(cudaSetDevice(d.ordinal));
+          SPE_TRY(launch_axpby(pdb, d.buf[BV2], d.buf[BV1], 1.0 / ee, -cc / ee, d.buf[ycur], d.st));
+        }
+        for (int kk = 1; kk < deg; ++kk) {   // Y_{k+1} = (2/e)(S Y_k - c Y_k) - Y_{k-1}
+          SPE_TRY(op_contract(ycur, pdb, BZ, NBUF, NBUF, false, sc0));
+          for (Dev& d : devs) {
+            SPE_CUDA(cudaSetDevice(d.ordinal));
+            SPE_TRY(launch_axpbypcz(pdb, d.buf[BZ], d.buf[ycur], d.buf[yprev], 2.0 / ee, -2.0 * cc / ee, -1.0, d.buf[yspare], d.st));
+          }
+          const Buf t = yprev; yprev = ycur; ycur = yspare; yspare = t;
+        }
+        std::vector<double> scale(kMaxCols, 1.0);
+        for (int c = 0; c < bq; ++c) scale[c] = 1.0 / cheb(deg, (sv2[c] - cc) / ee);
+        for (Dev& d : devs) {
+          SPE_CUDA(cudaSetDevice(d.ordinal));
+          SPE_CUDA(cudaMemcpyAsync(d.rho, scale.data(), bq * sizeof(double), cudaMemcpyHostToDevice, d.st));
+          SPE_TRY(launch_scale_columns(pdb, d.buf[ycur], d.rho, d.st));
+        }
+        SPE_TRY(sync_all());   // `scale` is a host temporary
+        SPE_TRY(op_polar(ycur, BQ, pdb, false, nullptr, 0, WARM_INIT));
+        if (cfg.verbose) fprintf(stderr, "[speigen] init pass %d: Chebyshev degree %d on [%.3e, %.3e]\n", passes, deg, lb, ub);
+      }
       {
         Dev& d = devs[0];
         int st = 0;

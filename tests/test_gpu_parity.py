@@ -289,6 +289,27 @@ def test_reference_testthat_behaviours():
     with pytest.raises(sb.SpEigenError, match="rank"): sb.spEigen(X[:3], 5, data=True)  # :69
 
 
+@pytest.mark.parametrize("decay", ["linear", "harmonic"])
+def test_initialiser_on_slowly_separating_spectra(decay):
+    """eigen()/svd() replacement (R/spEigen.R:68,76) on spectra without a spike: plain subspace iteration would need
+    thousands of passes (lambda_25 / lambda_10 = 0.994 for the linear case); the Chebyshev-filtered iteration converges."""
+    rng = np.random.default_rng(23)
+    m, q = 1200, 10
+    Qm, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    lam = 1.0 - np.arange(m) / (2.0 * m) if decay == "linear" else 1.0 / (1.0 + 0.05 * np.arange(m))
+    S = (Qm * lam[None, :]) @ Qm.T
+    S = (S + S.T) / 2
+    with sb.Solver(m, q, check_symmetric=1) as s:
+        s.load(S)
+        s.prepare()
+        info = s.init()
+        assert info["init_converged"] and info["init_passes"] < 200, info
+        r = s.run(rho=0.5)
+    ev = np.linalg.eigvalsh(S)[::-1][:q]
+    assert np.allclose(r["values"], ev, rtol=1e-11)
+    assert np.all(colwise_inner(r["standard_vectors"], Qm[:, :q]) > 1 - 1e-9)
+
+
 def test_not_pd_detected_beyond_the_top_block():
     """R/spEigen.R:77: a negative eigenvalue far below the leading block is found by the shifted power probe."""
     rng = np.random.default_rng(17)
