@@ -106,6 +106,9 @@ int speigen_run_c64(const double* X_interleaved, int64_t nrow, int64_t ncol, int
 int speigen_shutdown(void);
 const char* speigen_last_error(void);
 int speigen_abi_version(void);
+/* sizeof(speigen_cfg / speigen_out / speigen_problem) as compiled into the library: lets a foreign-language binding
+ * (ctypes, .Call glue built against an older header) detect a layout mismatch instead of corrupting memory. */
+int speigen_struct_sizes(int32_t* cfg_bytes, int32_t* out_bytes, int32_t* problem_bytes);
 int speigen_device_count(void);
 
 /* ---- host-only helpers (usable without a GPU) -------------------------------------------------- */

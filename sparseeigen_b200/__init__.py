@@ -116,6 +116,11 @@ def lib():
     L.speigen_solver_exchange_mode.argtypes = [C.c_void_p]
     L.speigen_solver_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
     L.speigen_solver_kernel_time.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int32)]
+    sz = (C.c_int32 * 3)()
+    L.speigen_struct_sizes(C.byref(sz, 0), C.byref(sz, 4), C.byref(sz, 8))
+    if (sz[0], sz[1], sz[2]) != (C.sizeof(Cfg), C.sizeof(Out), C.sizeof(Problem)):
+        raise ImportError(f"{path}: struct layout mismatch with include/speigen_b200.h "
+                          f"(library {tuple(sz)} vs binding {(C.sizeof(Cfg), C.sizeof(Out), C.sizeof(Problem))}); rebuild the library")
     _lib = L
     return L
 

@@ -59,6 +59,12 @@ void speigen_cfg_default(speigen_cfg* c) {
 
 const char* speigen_last_error(void) { return last_error(); }
 int speigen_abi_version(void) { return SPEIGEN_ABI_VERSION; }
+int speigen_struct_sizes(int32_t* cfg_bytes, int32_t* out_bytes, int32_t* problem_bytes) {
+  if (cfg_bytes) *cfg_bytes = static_cast<int32_t>(sizeof(speigen_cfg));
+  if (out_bytes) *out_bytes = static_cast<int32_t>(sizeof(speigen_out));
+  if (problem_bytes) *problem_bytes = static_cast<int32_t>(sizeof(speigen_problem));
+  return SPEIGEN_OK;
+}
 int speigen_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

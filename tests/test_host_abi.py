@@ -39,6 +39,17 @@ def test_r_glue_uses_only_exported_symbols():
         assert hasattr(L, s)
 
 
+def test_struct_layouts_match_the_header():
+    L = sb.lib()
+    sz = (ctypes.c_int32 * 3)()
+    assert L.speigen_struct_sizes(ctypes.byref(sz, 0), ctypes.byref(sz, 4), ctypes.byref(sz, 8)) == 0
+    assert tuple(sz) == (ctypes.sizeof(sb.Cfg), ctypes.sizeof(sb.Out), ctypes.sizeof(sb.Problem))
+    cfg = sb.default_cfg()
+    assert (cfg.max_iter, cfg.n_continuation, cfg.max_backtracks) == (1000, 10, 200)     # R/spEigen.R:47,94
+    assert (cfg.p1, cfg.pk, cfg.tol_factor, cfg.backtrack_slack) == (1.0, 7.0, 1e-2, 1e-9)   # :95-96,101,140
+    assert (cfg.rank_tol, cfg.pd_tol) == (1e-9, -1e-10) and cfg.p2p_exchange == 1 and cfg.pd_check_passes == 4
+
+
 def test_validate_args_matches_reference_conditions():
     L = sb.lib()
     assert L.speigen_validate_args(15, 10, 3.0, 0.5) == 0
