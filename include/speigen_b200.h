@@ -187,6 +187,92 @@ int speigen_solver_kernel_time(speigen_solver* s, double* ms_total, int32_t* lau
 int64_t speigen_solver_launch_count(speigen_solver* s);
 int speigen_solver_stream(speigen_solver* s, int32_t local_idx, void** cuda_stream);
 
+/* ==== SURVEY §8(f)-1: spEigenCov(S, q = 1, rho = 0.5, thres = 1e-9)                     R/spEigenCov.R:48 ========
+ * returning list(vectors = m x m, values = m, cov = m x m)                                R/spEigenCov.R:135
+ * Joint estimation of sparse eigenvectors and eigenvalues.  Real FP64 in this build (complex S returns
+ * SPEIGEN_ERR_UNSUPPORTED).  Additional status codes mirror its own stop() conditions. */
+#define SPEIGEN_ERR_Q_GT_M 8          /* "q should not be larger than m."               R/spEigenCov.R:55 */
+#define SPEIGEN_ERR_NOT_PSD 9         /* "The covariance matrix is not PSD."           R/spEigenCov.R:63 */
+#define SPEIGEN_ERR_LOW_RANK 10       /* "The covariance matrix is low-rank."          R/spEigenCov.R:65 */
+
+typedef struct speigencov_cfg {
+  int32_t max_iter;          /* 3000   R/spEigenCov.R:49 */
+  int32_t n_continuation;    /* K = 5  R/spEigenCov.R:80 (K+1 stages) */
+  double p1;                 /* 1      :81 */
+  double pk;                 /* 5      :82 */
+  double tol_factor;         /* 1e-1   :87 */
+  double eps_factor;         /* 1e-1   :88 */
+  double shift;              /* 1e-6   :69 */
+  double rank_tol;           /* 1e-9   :65 */
+  double psd_tol;            /* -1e-10 :63 (`<=`) */
+  double rho_scale;          /* 10     :73 */
+  int32_t check_symmetric;   /* 1 */
+  int32_t check_na;          /* 1 */
+  int32_t device;            /* CUDA ordinal */
+  int32_t jacobi_max_sweeps; /* 40: block one-sided Jacobi sweeps per SVD / EVD */
+  double jacobi_tol;         /* 0 -> sqrt(m) * eps: relative column orthogonality at which the sweeps stop */
+  int32_t polish;            /* 1: one Newton-Schulz step on the polar factor (orthonormal to working precision) */
+  int32_t verbose;
+} speigencov_cfg;
+void speigencov_cfg_default(speigencov_cfg* cfg);
+
+typedef struct speigencov_out {
+  double* vectors;           /* m x m column-major   R/spEigenCov.R:131-133 */
+  double* values;            /* m                    R/spEigenCov.R:107 */
+  double* cov;               /* m x m column-major   R/spEigenCov.R:135 (nullable: skipped) */
+  double* F;                 /* [trace_capacity] objective per iteration (optional; R/spEigenCov.R:114 computes but does not return it) */
+  int32_t* stage_of_k;       /* [trace_capacity] (optional) */
+  int32_t trace_capacity;
+  int32_t iterations;
+  int32_t eig_sweeps;        /* Jacobi sweeps of the initial eigen-decomposition */
+  int32_t svd_sweeps;        /* total Jacobi sweeps over all Procrustes updates */
+  int32_t gemms;             /* m x m x m GEMM launches */
+  double seconds_upload;
+  double seconds_init;
+  double seconds_loop;
+  double seconds_gemm;       /* device time inside the m x m x m GEMM launches (CUDA events) */
+} speigencov_out;
+
+/* one-shot drop-in call (host pointers): S is m x m column-major */
+int speigencov_run_f64(const double* S, int64_t nrow, int64_t ncol, double q, double rho, double thres,
+                       const speigencov_cfg* cfg, speigencov_out* out);
+/* R/spEigenCov.R:52-60 without the matrix scans (host only) */
+int speigencov_validate_args(int64_t nrow, int64_t ncol, double q, double rho);
+int speigencov_schedule(const speigencov_cfg* cfg, double* p, double* eps, double* tol);   /* :80-88, K+1 each */
+int speigencov_struct_sizes(int32_t* cfg_bytes, int32_t* out_bytes);   /* layout self-check for foreign-language bindings */
+/* eigvalAlgo(g, x, q), R/spEigenCov.R:164-338: ordered eigenvalue update (host only; xi_out[m]).
+ * Returns SPEIGEN_ERR_ARG where R would stop (q == 1 without violators reads an undefined `tmp` - this build pools {q} alone
+ * unless strict_r != 0). */
+int speigencov_eigval_algo(const double* g, int64_t m, double x, int32_t q, int32_t strict_r, double* xi_out);
+
+/* ---- dense kernel-level entry points (host column-major matrices in/out; used by the parity tests) -------------- */
+/* C (M x N) = alpha * op(A) * op(B).  a_kmajor != 0: A is K x M (op(A) = A^T), else M x K.  b_kmajor != 0: B is K x N, else N x K
+ * (op(B) = B^T).  symmetric != 0 (M == N, result known symmetric): upper tiles computed, mirrored.  ms_out (nullable): device time. */
+int speigen_dense_gemm(int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, int a_kmajor, const double* B,
+                       int64_t ldb, int b_kmajor, double* C, int64_t ldc, double alpha, int symmetric, int device,
+                       float* ms_out);
+/* Polar factor U = u v^T of svd(B) (R/spEigenCov.R:157-159), B is m x m. */
+int speigen_dense_polar(const double* B, int64_t m, double* U, int32_t polish, int device, int32_t* sweeps_out);
+/* Full symmetric eigen-decomposition, decreasing eigenvalues (eigen(S), R/spEigenCov.R:62). */
+int speigen_dense_eigh(const double* S, int64_t m, double* vectors, double* values, int device, int32_t* sweeps_out);
+/* `reps` back-to-back C = A^T B launches on resident random operands (M x N x K), CUDA events; ms_each[reps] */
+int speigen_dense_gemm_time(int64_t M, int64_t N, int64_t K, int a_kmajor, int b_kmajor, int symmetric, int device,
+                            int32_t reps, float* ms_each);
+
+/* ==== SURVEY §8(f)-2: the upstream cov(X) on the device ==========================================================
+ * Callers run spEigen(cov(X), q) (README.Rmd:108); forming S is a 2 n m^2 FP64 GEMM that would otherwise run in R
+ * and cross PCIe as 8 m^2 bytes.  X is n x m column-major on the host; S = cov(X) (centred, / (n - 1)) is formed by the
+ * GEMM kernel straight into each device's shard of the resident solver (covariance mode).  Follow with
+ * speigen_solver_prepare / _init / _run. */
+int speigen_solver_load_cov_of_data(speigen_solver* s, const double* X_host, int64_t n);
+/* the same from a device-resident X (n x m column-major, leading dimension ldx) on local device 0's ordinal */
+int speigen_solver_load_cov_of_data_device(speigen_solver* s, const double* X_dev, int64_t n, int64_t ldx);
+/* one-shot: spEigen(cov(X), q, rho, d = d, V = V0, thres = thres) */
+int speigen_run_cov_of_data_f64(const double* X, int64_t n, int64_t m, double q, double rho, const double* d,
+                                const double* V0, double thres, const speigen_cfg* cfg, speigen_out* out);
+/* cov(X) alone (host in/out): S_out is m x m column-major */
+int speigen_cov_f64(const double* X, int64_t n, int64_t m, double* S_out, int device, float* ms_gemm_out);
+
 #ifdef __cplusplus
 }
 #endif

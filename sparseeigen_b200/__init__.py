@@ -16,8 +16,9 @@ from typing import Optional
 
 import numpy as np
 
-__all__ = ["spEigen", "SpEigenError", "Solver", "lib", "library_path", "default_cfg", "schedule", "default_d",
-           "shard_range", "panel_pitch"]
+__all__ = ["spEigen", "spEigenCov", "SpEigenError", "Solver", "lib", "library_path", "default_cfg", "schedule", "default_d",
+           "shard_range", "panel_pitch", "default_cov_cfg", "cov_schedule", "eigval_algo", "dense_gemm", "dense_gemm_time",
+           "dense_polar", "dense_eigh", "cov"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libspeigen_b200.so"
@@ -53,6 +54,27 @@ class Out(C.Structure):
         ("iterations", C.c_int32), ("backtracks", C.c_int32), ("contractions", C.c_int32), ("init_passes", C.c_int32),
         ("init_converged", C.c_int32), ("init_residual", C.c_double), ("seconds_upload", C.c_double),
         ("seconds_init", C.c_double), ("seconds_loop", C.c_double),
+    ]
+
+
+class CovCfg(C.Structure):
+    """speigencov_cfg of include/speigen_b200.h (constants of R/spEigenCov.R:49,69,73,80-88)."""
+    _fields_ = [
+        ("max_iter", C.c_int32), ("n_continuation", C.c_int32), ("p1", C.c_double), ("pk", C.c_double),
+        ("tol_factor", C.c_double), ("eps_factor", C.c_double), ("shift", C.c_double), ("rank_tol", C.c_double),
+        ("psd_tol", C.c_double), ("rho_scale", C.c_double), ("check_symmetric", C.c_int32), ("check_na", C.c_int32),
+        ("device", C.c_int32), ("jacobi_max_sweeps", C.c_int32), ("jacobi_tol", C.c_double), ("polish", C.c_int32),
+        ("verbose", C.c_int32),
+    ]
+
+
+class CovOut(C.Structure):
+    _fields_ = [
+        ("vectors", C.POINTER(C.c_double)), ("values", C.POINTER(C.c_double)), ("cov", C.POINTER(C.c_double)),
+        ("F", C.POINTER(C.c_double)), ("stage_of_k", C.POINTER(C.c_int32)), ("trace_capacity", C.c_int32),
+        ("iterations", C.c_int32), ("eig_sweeps", C.c_int32), ("svd_sweeps", C.c_int32), ("gemms", C.c_int32),
+        ("seconds_upload", C.c_double), ("seconds_init", C.c_double), ("seconds_loop", C.c_double),
+        ("seconds_gemm", C.c_double),
     ]
 
 
@@ -116,11 +138,34 @@ def lib():
     L.speigen_solver_exchange_mode.argtypes = [C.c_void_p]
     L.speigen_solver_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
     L.speigen_solver_kernel_time.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int32)]
+    _ip = C.POINTER(C.c_int32)
+    _fp = C.POINTER(C.c_float)
+    L.speigencov_cfg_default.argtypes = [C.POINTER(CovCfg)]
+    L.speigencov_run_f64.argtypes = [_dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.POINTER(CovCfg),
+                                     C.POINTER(CovOut)]
+    L.speigencov_validate_args.argtypes = [C.c_int64, C.c_int64, C.c_double, C.c_double]
+    L.speigencov_schedule.argtypes = [C.POINTER(CovCfg), _dp, _dp, _dp]
+    L.speigencov_eigval_algo.argtypes = [_dp, C.c_int64, C.c_double, C.c_int32, C.c_int32, _dp]
+    L.speigen_dense_gemm.argtypes = [C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64, C.c_int, _dp, C.c_int64, C.c_int, _dp,
+                                     C.c_int64, C.c_double, C.c_int, C.c_int, _fp]
+    L.speigen_dense_gemm_time.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int32, _fp]
+    L.speigen_dense_polar.argtypes = [_dp, C.c_int64, _dp, C.c_int32, C.c_int, _ip]
+    L.speigen_dense_eigh.argtypes = [_dp, C.c_int64, _dp, _dp, C.c_int, _ip]
+    L.speigen_solver_load_cov_of_data.argtypes = [C.c_void_p, _dp, C.c_int64]
+    L.speigen_solver_load_cov_of_data_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    L.speigen_run_cov_of_data_f64.argtypes = [_dp, C.c_int64, C.c_int64, C.c_double, C.c_double, _dp, _dp, C.c_double,
+                                              C.POINTER(Cfg), C.POINTER(Out)]
+    L.speigen_cov_f64.argtypes = [_dp, C.c_int64, C.c_int64, _dp, C.c_int, _fp]
     sz = (C.c_int32 * 3)()
     L.speigen_struct_sizes(C.byref(sz, 0), C.byref(sz, 4), C.byref(sz, 8))
     if (sz[0], sz[1], sz[2]) != (C.sizeof(Cfg), C.sizeof(Out), C.sizeof(Problem)):
         raise ImportError(f"{path}: struct layout mismatch with include/speigen_b200.h "
                           f"(library {tuple(sz)} vs binding {(C.sizeof(Cfg), C.sizeof(Out), C.sizeof(Problem))}); rebuild the library")
+    sz2 = (C.c_int32 * 2)()
+    L.speigencov_struct_sizes(C.byref(sz2, 0), C.byref(sz2, 4))
+    if (sz2[0], sz2[1]) != (C.sizeof(CovCfg), C.sizeof(CovOut)):
+        raise ImportError(f"{path}: speigencov struct layout mismatch (library {tuple(sz2)} vs binding "
+                          f"{(C.sizeof(CovCfg), C.sizeof(CovOut))}); rebuild the library")
     _lib = L
     return L
 
@@ -218,13 +263,44 @@ class _OutBuffers:
 
 
 def spEigen(X, q=1, rho=0.5, data=False, d=None, V=None, thres=1e-9, *, n_gpus=1, cfg: Optional[Cfg] = None,
-            **cfg_overrides):
+            cov_of_data=False, **cfg_overrides):
     """Sparse (orthogonal) eigenvectors of a covariance or data matrix — drop-in for R/spEigen.R:46.
 
     Returns dict(vectors, standard_vectors, values) as the reference's list (R/spEigen.R:162) plus an
     'info' side channel (objective trajectory F_v, which the reference computes but does not return).
-    `d=None` / `V=None` play the role of R's NA defaults."""
+    `d=None` / `V=None` play the role of R's NA defaults.
+
+    cov_of_data=True evaluates the callers' `spEigen(cov(X), q, ...)` (README.Rmd:108) with X the n x m data matrix:
+    cov(X) is formed by the FP64 tensor-core GEMM straight into the device-resident shards, so the
+    m x m matrix never exists on the host.  Real X only."""
     X = np.asarray(X)
+    if cov_of_data:
+        if data:
+            raise SpEigenError(23, "cov_of_data=True means spEigen(cov(X), ...): use data=False")
+        if np.iscomplexobj(X) or X.ndim != 2:
+            raise SpEigenError(25, "cov_of_data needs a real n x m matrix")
+        n, m = X.shape
+        if m == 1:
+            raise SpEigenError(1, "Data is univariate!")
+        if _is_na(q) or _is_na(rho):
+            raise SpEigenError(2, "This function cannot handle NAs.")
+        L = lib()
+        _check(L.speigen_validate_args(m, m, float(q), float(rho)))
+        q = int(q)
+        Xf = _as_colmajor(X, False)
+        cfg = cfg or default_cfg()
+        cfg.n_gpus = n_gpus
+        for k, v in cfg_overrides.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown cfg field {k}")
+            setattr(cfg, k, v)
+        dd = None if d is None else np.ascontiguousarray(d, dtype=np.float64)
+        VV = None if V is None else _as_colmajor(np.asarray(V), False)
+        ob = _OutBuffers(m, q, False, trace_capacity=max(cfg.max_iter, 1))
+        _check(L.speigen_run_cov_of_data_f64(Xf.ctypes.data_as(_dp), n, m, float(q), float(rho), _ptr(dd),
+                                             None if VV is None else VV.ctypes.data_as(_dp), float(thres),
+                                             C.byref(cfg), C.byref(ob.c)))
+        return ob.result()
     if X.ndim == 1:                      # as.matrix(<vector>) is n x 1   (R/spEigen.R:50)
         X = X.reshape(-1, 1)
     if X.ndim != 2:
@@ -260,6 +336,133 @@ def spEigen(X, q=1, rho=0.5, data=False, d=None, V=None, thres=1e-9, *, n_gpus=1
             None if VV is None else VV.ctypes.data_as(_dp), float(thres), C.byref(cfg), C.byref(ob.c))
     _check(rc)
     return ob.result()
+
+
+def default_cov_cfg(**overrides) -> CovCfg:
+    cfg = CovCfg()
+    lib().speigencov_cfg_default(C.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise TypeError(f"unknown cfg field {k}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+def cov_schedule(cfg: Optional[CovCfg] = None):
+    """(p, eps, tol) of R/spEigenCov.R:80-88."""
+    cfg = cfg or default_cov_cfg()
+    n = cfg.n_continuation + 1
+    p, e, t = (np.empty(n) for _ in range(3))
+    _check(lib().speigencov_schedule(C.byref(cfg), _ptr(p), _ptr(e), _ptr(t)))
+    return p, e, t
+
+
+def eigval_algo(g, x, q, strict_r=False) -> np.ndarray:
+    """eigvalAlgo(g, x, q) of R/spEigenCov.R:164-338 (host-side part of the spEigenCov path)."""
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    out = np.empty_like(g)
+    _check(lib().speigencov_eigval_algo(_ptr(g), g.size, float(x), int(q), 1 if strict_r else 0, _ptr(out)))
+    return out
+
+
+def spEigenCov(S, q=1, rho=0.5, thres=1e-9, *, cfg: Optional[CovCfg] = None, want_cov=True, **cfg_overrides):
+    """Covariance estimation with sparse eigenvectors — drop-in for R/spEigenCov.R:48.
+
+    Returns dict(vectors m x m, values m, cov m x m) as the reference's list (R/spEigenCov.R:135) plus an 'info' side
+    channel (objective trajectory, sweep counts, timings).  Real S in this build."""
+    S = np.asarray(S)
+    if S.ndim == 0:
+        S = S.reshape(1, 1)
+    if S.ndim == 1:                      # as.matrix(<vector>) is n x 1   (R/spEigenCov.R:52)
+        S = S.reshape(-1, 1)
+    if S.ndim != 2:
+        raise SpEigenError(23, "S must be a matrix")
+    nrow, m = S.shape
+    L = lib()
+    qq = float("nan") if _is_na(q) else float(q)
+    rr = float("nan") if _is_na(rho) else float(rho)
+    _check(L.speigencov_validate_args(nrow, m, qq, rr))                               # :54-60
+    if np.iscomplexobj(S):
+        raise SpEigenError(25, "complex S is not supported by spEigenCov in this build")
+    Sf = _as_colmajor(S, False)
+    cfg = cfg or default_cov_cfg()
+    for k, v in cfg_overrides.items():
+        if not hasattr(cfg, k):
+            raise TypeError(f"unknown cfg field {k}")
+        setattr(cfg, k, v)
+    cap = max(cfg.max_iter, 1)
+    vectors = np.zeros((m, m), order="F")
+    values = np.zeros(m)
+    covm = np.zeros((m, m), order="F") if want_cov else None
+    F = np.zeros(cap)
+    stage = np.zeros(cap, dtype=np.int32)
+    o = CovOut()
+    o.vectors = vectors.ctypes.data_as(_dp)
+    o.values = _ptr(values)
+    o.cov = None if covm is None else covm.ctypes.data_as(_dp)
+    o.F = _ptr(F)
+    o.stage_of_k = stage.ctypes.data_as(C.POINTER(C.c_int32))
+    o.trace_capacity = cap
+    _check(L.speigencov_run_f64(Sf.ctypes.data_as(_dp), nrow, m, qq, rr, float(thres), C.byref(cfg), C.byref(o)))
+    k = min(o.iterations, cap)
+    info = dict(iterations=o.iterations, eig_sweeps=o.eig_sweeps, svd_sweeps=o.svd_sweeps, gemms=o.gemms,
+                seconds_upload=o.seconds_upload, seconds_init=o.seconds_init, seconds_loop=o.seconds_loop,
+                seconds_gemm=o.seconds_gemm, F=F[:k].copy(), stage_of_k=stage[:k].copy())
+    return dict(vectors=vectors, values=values, cov=covm, info=info)
+
+
+def dense_gemm(A, B, a_kmajor, b_kmajor, alpha=1.0, symmetric=False, device=0, return_ms=False):
+    """C = alpha * op(A) op(B) through the DMMA GEMM kernel.  a_kmajor: A is K x M (op(A) = A^T) else M x K;
+    b_kmajor: B is K x N else N x K (op(B) = B^T)."""
+    A = np.asfortranarray(A, dtype=np.float64)
+    B = np.asfortranarray(B, dtype=np.float64)
+    K, M = (A.shape if a_kmajor else A.shape[::-1])
+    Kb, N = (B.shape if b_kmajor else B.shape[::-1])
+    if K != Kb:
+        raise SpEigenError(23, "inner dimensions differ")
+    Cm = np.zeros((M, N), order="F")
+    ms = C.c_float(0.0)
+    _check(lib().speigen_dense_gemm(M, N, K, _ptr(A), A.shape[0], 1 if a_kmajor else 0, _ptr(B), B.shape[0],
+                                    1 if b_kmajor else 0, _ptr(Cm), M, float(alpha), 1 if symmetric else 0, device,
+                                    C.byref(ms)))
+    return (Cm, ms.value) if return_ms else Cm
+
+
+def dense_gemm_time(M, N, K, a_kmajor=True, b_kmajor=True, symmetric=False, reps=5, device=0) -> np.ndarray:
+    ms = (C.c_float * reps)()
+    _check(lib().speigen_dense_gemm_time(M, N, K, int(a_kmajor), int(b_kmajor), int(symmetric), device, reps, ms))
+    return np.array(ms[:], dtype=np.float64)
+
+
+def dense_polar(B, polish=True, device=0):
+    """(U, sweeps): U = u v^T of svd(B) (R/spEigenCov.R:157-159) by the block one-sided Jacobi kernels."""
+    B = np.asfortranarray(B, dtype=np.float64)
+    m = B.shape[0]
+    U = np.zeros((m, m), order="F")
+    sw = C.c_int32(0)
+    _check(lib().speigen_dense_polar(_ptr(B), m, _ptr(U), 1 if polish else 0, device, C.byref(sw)))
+    return U, sw.value
+
+
+def dense_eigh(S, device=0):
+    """(values decreasing, vectors, sweeps) as eigen(S) (R/spEigenCov.R:62)."""
+    S = np.asfortranarray(S, dtype=np.float64)
+    m = S.shape[0]
+    V = np.zeros((m, m), order="F")
+    w = np.zeros(m)
+    sw = C.c_int32(0)
+    _check(lib().speigen_dense_eigh(_ptr(S), m, _ptr(V), _ptr(w), device, C.byref(sw)))
+    return w, V, sw.value
+
+
+def cov(X, device=0, return_ms=False):
+    """cov(X) (column-centred, / (n-1)) formed on the device by the symmetric DMMA GEMM."""
+    X = np.asfortranarray(X, dtype=np.float64)
+    n, m = X.shape
+    S = np.zeros((m, m), order="F")
+    ms = C.c_float(0.0)
+    _check(lib().speigen_cov_f64(_ptr(X), n, m, _ptr(S), device, C.byref(ms)))
+    return (S, ms.value) if return_ms else S
 
 
 class Solver:
@@ -315,6 +518,14 @@ class Solver:
     def load(self, X):
         Xf = _as_colmajor(np.asarray(X), self.cplx)
         _check(self.L.speigen_solver_load_host(self.h, Xf.ctypes.data_as(_dp)))
+
+    def load_cov_of_data(self, X):
+        """S = cov(X) formed on the device(s) straight into the shard buffers (covariance-mode solver)."""
+        Xf = _as_colmajor(np.asarray(X), False)
+        _check(self.L.speigen_solver_load_cov_of_data(self.h, Xf.ctypes.data_as(_dp), Xf.shape[0]))
+
+    def load_cov_of_data_device(self, dev_ptr: int, n: int, ldx: int):
+        _check(self.L.speigen_solver_load_cov_of_data_device(self.h, C.c_void_p(dev_ptr), n, ldx))
 
     def shard_buffer(self, local_idx=0):
         p = C.c_void_p()

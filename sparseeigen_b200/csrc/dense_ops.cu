@@ -1,0 +1,793 @@
+// Dense m x m FP64 kernels for spEigenCov() and the on-device cov(X)  (see dense_ops.cuh).
+//
+// k_gemm<AK,BK>: C = alpha * op(A) * op(B).  128 x 128 CTA tile, 32-deep k-stages, 3-stage TMA/mbarrier ring, one
+// producer warp + 8 consumer warps (2 x 4, warp tile 64 x 32) issuing mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05 has
+// no FP64 kind).  An operand whose contracted index is contiguous is staged as 128B-swizzled boxes of 16 doubles x 128
+// rows and read with the conflict-free row permutation of the streamed contraction (contract.cu); an operand whose
+// free index is contiguous is staged as one un-swizzled box of 132 x 32 doubles (pitch == 4 mod 16 -> conflict-free
+// LDS.64 for the m8n8k4 fragment shape).  Persistent over tiles (grid = #SMs), grouped rasterisation for L2 reuse.
+// Bound: FP64 tensor pipe (37.0 TFLOP/s measured, tools/microbench/fp64_pipes.cu).
+#include "dense_ops.cuh"
+#include "../../include/speigen_b200.h"
+#include <cmath>
+
+namespace speigen {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+//                                                    GEMM
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kGW = 8;                        // consumer warps
+constexpr int kGThreads = (kGW + 1) * 32;
+constexpr int kGMT = 8, kGNT = 4;             // m-tiles / n-tiles (8 wide) per warp
+constexpr int kGStages = 3;
+constexpr uint32_t kOpStageBytes = 34816;     // per operand and stage: two swizzled 16 KB boxes or one 132 x 32 box (33 792 B)
+constexpr uint32_t kGStageBytes = 2 * kOpStageBytes;
+constexpr int kMPitch = kGemmTM + 4;          // 132
+constexpr uint32_t kBoxK = 16 * 128 * 8;      // swizzled box bytes
+constexpr int kRasterGroup = 16;
+
+struct GemmParams {
+  int64_t M, N, K;
+  int tiles_m, tiles_n, ksteps;
+  int64_t ntiles;
+  double* C;
+  int64_t ldc;
+  double alpha, beta;
+  int symmetric;
+};
+
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+__device__ __forceinline__ void tile_coords(const GemmParams& prm, int64_t t, int& tm, int& tn) {
+  if (prm.symmetric) {   // upper-triangular tiles only: t = tn (tn + 1) / 2 + tm, tm <= tn
+    int64_t n = static_cast<int64_t>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
+    while (n * (n + 1) / 2 > t) --n;
+    while ((n + 1) * (n + 2) / 2 <= t) ++n;
+    tn = static_cast<int>(n);
+    tm = static_cast<int>(t - n * (n + 1) / 2);
+  } else {               // groups of kRasterGroup row tiles swept along n: concurrently running CTAs share operand tiles in L2
+    const int64_t per_group = static_cast<int64_t>(kRasterGroup) * prm.tiles_n;
+    const int g = static_cast<int>(t / per_group);
+    const int first_m = g * kRasterGroup;
+    const int gsz = min(prm.tiles_m - first_m, kRasterGroup);
+    const int64_t r = t - static_cast<int64_t>(g) * per_group;
+    tm = first_m + static_cast<int>(r % gsz);
+    tn = static_cast<int>(r / gsz);
+  }
+}
+
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(kGThreads, 1)
+k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams prm) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_bar[kGStages];
+  __shared__ __align__(8) uint64_t empty_bar[kGStages];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < kGStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kGW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  constexpr uint32_t kBytesA = AK ? 2 * kBoxK : kMPitch * kGemmTK * 8;
+  constexpr uint32_t kBytesB = BK ? 2 * kBoxK : kMPitch * kGemmTK * 8;
+
+  if (warp == kGW) {
+    // ------------------------------- producer warp -------------------------------
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_normal();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < prm.ntiles; t += gridDim.x) {
+        int tm, tn;
+        tile_coords(prm, t, tm, tn);
+        for (int ks = 0; ks < prm.ksteps; ++ks) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          unsigned char* sA = smem + static_cast<size_t>(stage) * kGStageBytes;
+          unsigned char* sB = sA + kOpStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], kBytesA + kBytesB);
+          if (AK) {
+            tma_load_2d(sA, &tmA, ks * kGemmTK, tm * kGemmTM, &full_bar[stage], pol);
+            tma_load_2d(sA + kBoxK, &tmA, ks * kGemmTK + 16, tm * kGemmTM, &full_bar[stage], pol);
+          } else {
+            tma_load_2d(sA, &tmA, tm * kGemmTM, ks * kGemmTK, &full_bar[stage], pol);
+          }
+          if (BK) {
+            tma_load_2d(sB, &tmB, ks * kGemmTK, tn * kGemmTN, &full_bar[stage], pol);
+            tma_load_2d(sB + kBoxK, &tmB, ks * kGemmTK + 16, tn * kGemmTN, &full_bar[stage], pol);
+          } else {
+            tma_load_2d(sB, &tmB, tn * kGemmTN, ks * kGemmTK, &full_bar[stage], pol);
+          }
+          if (++stage == kGStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+
+  // --------------------------------- consumer warps ---------------------------------
+  const int wm = warp & 1;                       // 2 warps along m (64 rows each)
+  const int wn = warp >> 1;                      // 4 warps along n (32 columns each)
+  const int grp = lane >> 2;
+  const int kk = lane & 3;
+  const int pr = 2 * (grp & 3) + (grp >> 2);     // fragment row -> tile row permutation of the swizzled layout
+
+  uint32_t a_off[kGMT], b_off[kGNT];
+  int a_r7[kGMT], b_r7[kGNT];
+#pragma unroll
+  for (int mt = 0; mt < kGMT; ++mt) {
+    const int il = wm * 64 + mt * 8 + (AK ? pr : grp);
+    a_off[mt] = AK ? (il * 128 + (kk & 1) * 8) : ((kk * kMPitch + il) * 8);
+    a_r7[mt] = il & 7;
+  }
+#pragma unroll
+  for (int nt = 0; nt < kGNT; ++nt) {
+    const int nl = wn * 32 + nt * 8 + (BK ? pr : grp);
+    b_off[nt] = BK ? (nl * 128 + (kk & 1) * 8) : ((kk * kMPitch + nl) * 8);
+    b_r7[nt] = nl & 7;
+  }
+
+  double acc[kGMT][kGNT][2];
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int64_t t = blockIdx.x; t < prm.ntiles; t += gridDim.x) {
+    int tm, tn;
+    tile_coords(prm, t, tm, tn);
+#pragma unroll
+    for (int mt = 0; mt < kGMT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < kGNT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    for (int ks = 0; ks < prm.ksteps; ++ks) {
+      mbar_wait(&full_bar[stage], phase);
+      const unsigned char* sA = smem + static_cast<size_t>(stage) * kGStageBytes;
+      const unsigned char* sB = sA + kOpStageBytes;
+#pragma unroll
+      for (int k4 = 0; k4 < kGemmTK / 4; ++k4) {
+        const int chunk = 2 * (k4 & 3) + (kk >> 1);            // 16-byte chunk inside the 128-byte swizzled row
+        const uint32_t boxo = (k4 >> 2) * kBoxK;
+        const uint32_t mo = k4 * 4 * kMPitch * 8;
+        double af[kGMT], bf[kGNT];
+#pragma unroll
+        for (int mt = 0; mt < kGMT; ++mt)
+          af[mt] = AK ? *reinterpret_cast<const double*>(sA + boxo + a_off[mt] + ((chunk ^ a_r7[mt]) << 4))
+                      : *reinterpret_cast<const double*>(sA + mo + a_off[mt]);
+#pragma unroll
+        for (int nt = 0; nt < kGNT; ++nt)
+          bf[nt] = BK ? *reinterpret_cast<const double*>(sB + boxo + b_off[nt] + ((chunk ^ b_r7[nt]) << 4))
+                      : *reinterpret_cast<const double*>(sB + mo + b_off[nt]);
+#pragma unroll
+        for (int mt = 0; mt < kGMT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < kGNT; ++nt) dmma_884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == kGStages) { stage = 0; phase ^= 1u; }
+    }
+
+    // epilogue (the producer is already prefetching the next tile's stages)
+    const bool mirror = prm.symmetric && (tm != tn);
+#pragma unroll
+    for (int mt = 0; mt < kGMT; ++mt) {
+      const int64_t row = static_cast<int64_t>(tm) * kGemmTM + wm * 64 + mt * 8 + (AK ? pr : grp);
+#pragma unroll
+      for (int nt = 0; nt < kGNT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int fc = 2 * kk + e;
+          const int64_t col = static_cast<int64_t>(tn) * kGemmTN + wn * 32 + nt * 8 + (BK ? (2 * (fc & 3) + (fc >> 2)) : fc);
+          if (row < prm.M && col < prm.N) {
+            double v = prm.alpha * acc[mt][nt][e];
+            double* dst = prm.C + row + col * prm.ldc;
+            if (prm.beta != 0.0) v += prm.beta * (*dst);
+            *dst = v;
+            if (mirror) prm.C[col + row * prm.ldc] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// inner = contiguous extent of the stored matrix, outer = number of columns of the stored matrix
+int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int64_t free_extent, int64_t K) {
+  PFN_encodeTiled enc = encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return SPEIGEN_ERR_CUDA; }
+  if ((op.ld & 1) || (reinterpret_cast<uintptr_t>(op.ptr) & 15)) {
+    set_error("GEMM operand must be 16-byte aligned with an even leading dimension");
+    return SPEIGEN_ERR_ARG;
+  }
+  cuuint64_t gdim[2];
+  cuuint32_t box[2];
+  CUtensorMapSwizzle swz;
+  if (op.kmajor) { gdim[0] = K; gdim[1] = free_extent; box[0] = 16; box[1] = 128; swz = CU_TENSOR_MAP_SWIZZLE_128B; }
+  else { gdim[0] = free_extent; gdim[1] = K; box[0] = kMPitch; box[1] = kGemmTK; swz = CU_TENSOR_MAP_SWIZZLE_NONE; }
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(op.ld) * sizeof(double)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(op.ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (GEMM operand) failed with CUresult %d (free=%lld K=%lld ld=%lld kmajor=%d)", (int)r,
+              (long long)free_extent, (long long)K, (long long)op.ld, op.kmajor);
+    return SPEIGEN_ERR_CUDA;
+  }
+  return SPEIGEN_OK;
+}
+
+template <bool AK, bool BK>
+int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& prm, int grid, cudaStream_t st) {
+  static bool attr_set_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];
+  const size_t smem = static_cast<size_t>(kGStages) * kGStageBytes;
+  if (!attr_set) {
+    SPE_CUDA(cudaFuncSetAttribute(k_gemm<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_gemm<AK, BK><<<grid, kGThreads, smem, st>>>(ta, tb, prm);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+//                                     block one-sided Jacobi: panel kernels
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kTilePitch = kJRows + 4;   // 132: column pitch of a staged 128-row x 64-column tile
+constexpr int kWPitch = kJP + 4;         // 68
+
+__device__ __forceinline__ void load_panel_tile(const double* Mat, int64_t ld, int64_t c0, int64_t r0, double* tile) {
+  // 64 columns x 128 rows, coalesced double2 reads, stored column by column with pitch 132
+  for (int idx = threadIdx.x; idx < kJP * (kJRows / 2); idx += blockDim.x) {
+    const int c = idx / (kJRows / 2);
+    const int r2 = idx - c * (kJRows / 2);
+    const double2 v = *reinterpret_cast<const double2*>(Mat + (c0 + c) * ld + r0 + 2 * r2);
+    *reinterpret_cast<double2*>(tile + c * kTilePitch + 2 * r2) = v;
+  }
+}
+
+// partial Gram of panel p over row split s:  G = Xp^T Xp  (64 x 64)
+__global__ void __launch_bounds__(256) k_jgram(const double* X, int64_t mp, int64_t ld, int col0, int nsplit, double* gram_part) {
+  extern __shared__ __align__(16) double sm_dyn[];
+  double* tile = sm_dyn;
+  const int p = blockIdx.x, s = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 2, kk = lane & 3;
+  const int64_t c0 = col0 + static_cast<int64_t>(kJP) * p;
+  const int chunks = static_cast<int>(mp / kJRows);
+  const int ch0 = static_cast<int>(static_cast<int64_t>(s) * chunks / nsplit);
+  const int ch1 = static_cast<int>(static_cast<int64_t>(s + 1) * chunks / nsplit);
+  double acc[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+  for (int ch = ch0; ch < ch1; ++ch) {
+    __syncthreads();
+    load_panel_tile(X, ld, c0, static_cast<int64_t>(ch) * kJRows, tile);
+    __syncthreads();
+    const double* ta = tile + (warp * 8 + grp) * kTilePitch + kk;
+#pragma unroll 4
+    for (int k4 = 0; k4 < kJRows / 4; ++k4) {
+      const double af = ta[k4 * 4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const double bf = tile[(nt * 8 + grp) * kTilePitch + k4 * 4 + kk];
+        dmma_884(acc[nt][0], acc[nt][1], af, bf);
+      }
+    }
+  }
+  double* out = gram_part + (static_cast<size_t>(p) * nsplit + s) * (kJP * kJP);
+  const int j1 = warp * 8 + grp;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    out[(nt * 8 + 2 * kk) * kJP + j1] = acc[nt][0];
+    out[(nt * 8 + 2 * kk + 1) * kJP + j1] = acc[nt][1];
+  }
+}
+
+// Two-sided cyclic Jacobi (round-robin parallel ordering, one warp per pair) on the 64 x 64 panel Gram matrix.
+// Writes the accumulated rotation with the two 32-column blocks exchanged (odd-even block ordering).
+constexpr int kEigPitch = kJP + 1;   // 65
+__global__ void __launch_bounds__(1024) k_jeig(const double* gram_part, int nsplit, double* wp, double* offmax) {
+  extern __shared__ __align__(16) double sm_dyn[];
+  double* G = sm_dyn;                          // [64][65]
+  double* W = sm_dyn + kJP * kEigPitch;        // [64][65]
+  __shared__ double s_red[32];
+  const int p = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double* part = gram_part + static_cast<size_t>(p) * nsplit * (kJP * kJP);
+  for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < nsplit; ++k) s += part[static_cast<size_t>(k) * (kJP * kJP) + idx];   // fixed order
+    const int c = idx / kJP, r = idx - c * kJP;
+    G[r * kEigPitch + c] = s;
+    W[r * kEigPitch + c] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  // relative off-diagonal measure of this panel (before rotating)
+  double mx = 0.0;
+  for (int rr = 0; rr < 2; ++rr) {
+    const int i = warp * 2 + rr;
+    const double gii = G[i * kEigPitch + i];
+    for (int j = lane; j < kJP; j += 32) {
+      if (j == i) continue;
+      const double gij = fabs(G[i * kEigPitch + j]);
+      if (gij == 0.0) continue;
+      const double den = sqrt(fabs(gii) * fabs(G[j * kEigPitch + j]));
+      const double r = den > 0.0 ? gij / den : 1.0e300;
+      mx = fmax(mx, r);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    double v = s_red[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) {
+      s_red[0] = v;
+      atomicMax(reinterpret_cast<unsigned long long*>(offmax), static_cast<unsigned long long>(__double_as_longlong(v)));
+    }
+  }
+  __syncthreads();
+  const double panel_off = s_red[0];
+  const double eps = 2.220446049250313e-16;
+  if (panel_off > eps) {
+    for (int sweep = 0; sweep < 60; ++sweep) {
+      int any = 0;
+      for (int r = 0; r < kJP - 1; ++r) {
+        int a, b;
+        if (warp == 0) { a = kJP - 1; b = r; }
+        else { a = (r + warp) % (kJP - 1); b = (r - warp + (kJP - 1)) % (kJP - 1); }
+        const int pi = min(a, b), qi = max(a, b);
+        // (pi,pi), (qi,qi), (pi,qi) are written only by this warp in this round -> no barrier needed before reading
+        const double gpp = G[pi * kEigPitch + pi], gqq = G[qi * kEigPitch + qi], gpq = G[pi * kEigPitch + qi];
+        double c = 1.0, s = 0.0;
+        const bool rot = fabs(gpq) > eps * sqrt(fabs(gpp) * fabs(gqq));
+        if (rot) {
+          const double zeta = (gqq - gpp) / (2.0 * gpq);
+          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(1.0 + tt * tt);
+          s = c * tt;
+          any = 1;
+        }
+        // column phase: columns pi, qi of G and W
+        if (rot) {
+          for (int i = lane; i < kJP; i += 32) {
+            const double g1 = G[i * kEigPitch + pi], g2 = G[i * kEigPitch + qi];
+            G[i * kEigPitch + pi] = c * g1 - s * g2;
+            G[i * kEigPitch + qi] = s * g1 + c * g2;
+            const double w1 = W[i * kEigPitch + pi], w2 = W[i * kEigPitch + qi];
+            W[i * kEigPitch + pi] = c * w1 - s * w2;
+            W[i * kEigPitch + qi] = s * w1 + c * w2;
+          }
+        }
+        __syncthreads();
+        // row phase: rows pi, qi of G
+        if (rot) {
+          for (int j = lane; j < kJP; j += 32) {
+            const double g1 = G[pi * kEigPitch + j], g2 = G[qi * kEigPitch + j];
+            G[pi * kEigPitch + j] = c * g1 - s * g2;
+            G[qi * kEigPitch + j] = s * g1 + c * g2;
+          }
+          __syncwarp();
+          if (lane == 0) { G[pi * kEigPitch + qi] = 0.0; G[qi * kEigPitch + pi] = 0.0; }
+        }
+        __syncthreads();
+      }
+      if (!__syncthreads_or(any)) break;
+    }
+  }
+  // out[:, j] = W[:, (j + 32) mod 64]  (column-major 64 x 64)
+  double* out = wp + static_cast<size_t>(p) * (kJP * kJP);
+  for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) {
+    const int j = idx / kJP, k = idx - j * kJP;
+    out[idx] = W[k * kEigPitch + ((j + kJB) & (kJP - 1))];
+  }
+}
+
+// Mat[:, panel p] <- Mat[:, panel p] * Wp   for Mat in {X, W} (blockIdx.z), row chunk blockIdx.y; in place
+__global__ void __launch_bounds__(256) k_japply(double* X, double* Wt, int64_t ld, int col0, const double* wp) {
+  extern __shared__ __align__(16) double sm_dyn[];
+  double* tile = sm_dyn;                         // [64][132]
+  double* sW = sm_dyn + kJP * kTilePitch;        // [64 n][68]: sW[n][k] = Wp[k][n]
+  double* Mat = blockIdx.z == 0 ? X : Wt;
+  const int p = blockIdx.x;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kJRows;
+  const int64_t c0 = col0 + static_cast<int64_t>(kJP) * p;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 2, kk = lane & 3;
+  load_panel_tile(Mat, ld, c0, r0, tile);
+  const double* w = wp + static_cast<size_t>(p) * (kJP * kJP);
+  for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) {
+    const int n = idx / kJP, k = idx - n * kJP;   // column-major: element (k, n)
+    sW[n * kWPitch + k] = w[idx];
+  }
+  __syncthreads();
+  double acc[2][8][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll 4
+  for (int k4 = 0; k4 < kJP / 4; ++k4) {
+    const int k = k4 * 4 + kk;
+    const double a0 = tile[k * kTilePitch + (warp * 2) * 8 + grp];
+    const double a1 = tile[k * kTilePitch + (warp * 2 + 1) * 8 + grp];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const double bf = sW[(nt * 8 + grp) * kWPitch + k];
+      dmma_884(acc[0][nt][0], acc[0][nt][1], a0, bf);
+      dmma_884(acc[1][nt][0], acc[1][nt][1], a1, bf);
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int64_t row = r0 + (warp * 2 + mt) * 8 + grp;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      Mat[(c0 + nt * 8 + 2 * kk) * ld + row] = acc[mt][nt][0];
+      Mat[(c0 + nt * 8 + 2 * kk + 1) * ld + row] = acc[mt][nt][1];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+//                                     column-major helpers
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kCT = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+  __syncthreads();
+  return s;   // valid on thread 0
+}
+__device__ __forceinline__ double block_min(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = red[0];
+  if (threadIdx.x == 0)
+    for (int w = 1; w < (blockDim.x >> 5); ++w) s = fmin(s, red[w]);
+  __syncthreads();
+  return s;
+}
+
+__global__ void __launch_bounds__(kCT) k_cm_coldots(const double* A, const double* B, int64_t rows, int64_t ld, double* out) {
+  __shared__ double red[kCT / 32];
+  const int64_t j = blockIdx.x;
+  const double* a = A + j * ld;
+  const double* b = B + j * ld;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < rows; i += kCT) s = fma(a[i], b[i], s);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[j] = s;
+}
+__global__ void __launch_bounds__(kCT) k_cm_colabsmin(const double* A, int64_t rows, int64_t ld, double* out) {
+  __shared__ double red[kCT / 32];
+  const int64_t j = blockIdx.x;
+  const double* a = A + j * ld;
+  double s = 1.0e300;
+  for (int64_t i = threadIdx.x; i < rows; i += kCT) s = fmin(s, fabs(a[i]));
+  s = block_min(s, red);
+  if (threadIdx.x == 0) out[j] = s;
+}
+__global__ void __launch_bounds__(kCT) k_cm_penalty(const double* A, int64_t rows, int64_t ld, StageConsts sc, double* out) {
+  __shared__ double red[kCT / 32];
+  const int64_t j = blockIdx.x;
+  const double* a = A + j * ld;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < rows; i += kCT) {
+    const double v = fabs(a[i]);
+    // R/spEigenCov.R:111-112
+    s += (v <= sc.eps) ? v * v / (sc.eps * sc.c2) : log((sc.p + v) / (sc.p + sc.eps)) / sc.c1 + sc.eps / sc.c2;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[j] = s;
+}
+__global__ void k_cm_scale_cols(double* A, int64_t rows, int64_t cols, int64_t ld, const double* s, int inv) {
+  const int64_t j = blockIdx.y;
+  const double f = inv ? 1.0 / s[j] : s[j];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    A[j * ld + i] *= f;
+}
+__global__ void k_cm_gather_cols(const double* In, int64_t rows, int64_t ld, const int* perm, double* Out) {
+  const int64_t j = blockIdx.y;
+  const int64_t src = perm[j];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    Out[j * ld + i] = In[src * ld + i];
+}
+__global__ void k_cm_pad_copy(const double* Src, int64_t m, int64_t lds, double* Dst, int64_t mp, int64_t ld, double shift,
+                              double pad_diag) {
+  const int64_t j = blockIdx.y;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < mp; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    double v = 0.0;
+    if (i < m && j < m) v = Src[j * lds + i] - (i == j ? shift : 0.0);
+    else if (i == j) v = pad_diag;
+    Dst[j * ld + i] = v;
+  }
+}
+__global__ void k_cm_build_target(const double* V, const double* T, const double* inv_xi, const double* rho, const double* absmin,
+                                  int q, StageConsts sc, int64_t m, int64_t mp, int64_t ld, double* B) {
+  const int64_t j = blockIdx.y;
+  const double ixi = j < m ? inv_xi[j] : 0.0;
+  const bool sparse = j < q;
+  const double wmax = sparse ? weight_of_abs(absmin[j], sc) : 0.0;   // column max of the weights = w(min |V|)  (R/spEigenCov.R:153)
+  const double rj = sparse ? rho[j] : 0.0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < mp; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    double v;
+    if (i < m && j < m) {
+      const double h2 = T[j * ld + i] * ixi;                          // (S_hat V) diag(1/Xi)            :154
+      double h1 = 0.0;
+      if (sparse) {
+        const double vij = V[j * ld + i];
+        h1 = (weight_of_abs(fabs(vij), sc) - wmax) * vij * rj;        // :147-153
+      }
+      v = -(h1 + h2);                                                 // :157
+    } else {
+      v = (i == j) ? 1.0 : 0.0;
+    }
+    B[j * ld + i] = v;
+  }
+}
+__global__ void k_cm_ns_matrix(const double* G, int64_t mp, int64_t ld, double* M) {
+  const int64_t j = blockIdx.y;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < mp; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    M[j * ld + i] = (i == j ? 1.5 : 0.0) - 0.5 * G[j * ld + i];
+}
+__global__ void __launch_bounds__(kCT) k_cm_thres_norms(const double* V, int64_t m, int64_t ld, double thres, double* nrm2) {
+  __shared__ double red[kCT / 32];
+  const int64_t j = blockIdx.x;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += kCT) {
+    const double v = V[j * ld + i];
+    if (!(fabs(v) < thres)) s = fma(v, v, s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) nrm2[j] = s;
+}
+__global__ void k_cm_thres_scale(const double* V, int64_t m, int64_t ld, double thres, const double* rs, const double* cs,
+                                 double* Out, int64_t ldo) {
+  const int64_t j = blockIdx.y;
+  const double cj = cs ? cs[j] : 1.0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < m; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    double v = V[j * ld + i];
+    if (fabs(v) < thres) v = 0.0;
+    Out[j * ldo + i] = v * (rs ? rs[i] : 1.0) * cj;
+  }
+}
+__global__ void __launch_bounds__(kCT) k_cm_scan_sym(const double* S, int64_t m, int64_t ld, double* part) {
+  __shared__ double red[kCT / 32];
+  const int64_t j = blockIdx.x;
+  double d = 0.0, a = 0.0, nn = 0.0, sq = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += kCT) {
+    const double v = S[j * ld + i];
+    const double t = S[i * ld + j];
+    if (v != v) nn += 1.0;
+    else { d += fabs(v - t); a += fabs(v); sq = fma(v, v, sq); }
+  }
+  d = block_sum(d, red);
+  a = block_sum(a, red);
+  nn = block_sum(nn, red);
+  sq = block_sum(sq, red);
+  if (threadIdx.x == 0) { part[j * 4 + 0] = d; part[j * 4 + 1] = a; part[j * 4 + 2] = nn; part[j * 4 + 3] = sq; }
+}
+__global__ void __launch_bounds__(kCT) k_cm_sum4(const double* part, int64_t n, double* out4) {
+  __shared__ double red[kCT / 32];
+  for (int e = 0; e < 4; ++e) {
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += kCT) s += part[i * 4 + e];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out4[e] = s;
+  }
+}
+__global__ void __launch_bounds__(kCT) k_cm_colsums(const double* X, int64_t n, int64_t ld, double* out) {
+  __shared__ double red[kCT / 32];
+  const int64_t j = blockIdx.x;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += kCT) s += X[j * ld + i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[j] = s;
+}
+__global__ void k_cm_center(double* X, int64_t n, int64_t ld, const double* sums, double inv_n) {
+  const int64_t j = blockIdx.y;
+  const double mu = sums[j] * inv_n;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    X[j * ld + i] -= mu;
+}
+
+inline dim3 grid2(int64_t rows, int64_t cols) {
+  int64_t bx = (rows + 255) / 256;
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  return dim3(static_cast<unsigned>(bx), static_cast<unsigned>(cols), 1);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+int launch_gemm(int64_t M, int64_t N, int64_t K, const GemmOperand& A, const GemmOperand& B, double* C, int64_t ldc,
+                const GemmEpilogue& epi, int num_sms, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return SPEIGEN_OK;
+  CUtensorMap ta, tb;
+  int rc = make_operand_map(&ta, A, M, K);
+  if (rc != SPEIGEN_OK) return rc;
+  rc = make_operand_map(&tb, B, N, K);
+  if (rc != SPEIGEN_OK) return rc;
+  GemmParams prm;
+  prm.M = M; prm.N = N; prm.K = K;
+  prm.tiles_m = static_cast<int>((M + kGemmTM - 1) / kGemmTM);
+  prm.tiles_n = static_cast<int>((N + kGemmTN - 1) / kGemmTN);
+  prm.ksteps = static_cast<int>((K + kGemmTK - 1) / kGemmTK);
+  prm.symmetric = (epi.symmetric && M == N) ? 1 : 0;
+  prm.ntiles = prm.symmetric ? static_cast<int64_t>(prm.tiles_n) * (prm.tiles_n + 1) / 2
+                             : static_cast<int64_t>(prm.tiles_m) * prm.tiles_n;
+  prm.C = C; prm.ldc = ldc; prm.alpha = epi.alpha; prm.beta = epi.beta;
+  if (prm.symmetric && epi.beta != 0.0) { set_error("symmetric GEMM epilogue does not support beta"); return SPEIGEN_ERR_ARG; }
+  const int grid = static_cast<int>(prm.ntiles < num_sms ? prm.ntiles : num_sms);
+  if (A.kmajor && B.kmajor) return launch_gemm_t<true, true>(ta, tb, prm, grid, st);
+  if (A.kmajor && !B.kmajor) return launch_gemm_t<true, false>(ta, tb, prm, grid, st);
+  if (!A.kmajor && B.kmajor) return launch_gemm_t<false, true>(ta, tb, prm, grid, st);
+  return launch_gemm_t<false, false>(ta, tb, prm, grid, st);
+}
+
+int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity, const JacobiWork& jw, cudaStream_t st) {
+  const int nblocks = static_cast<int>(mp / kJB);
+  const int npanels = nblocks / 2 - (parity ? 1 : 0);
+  if (npanels <= 0) return SPEIGEN_OK;
+  const int col0 = parity ? kJB : 0;
+  static bool attr_set_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];
+  const size_t smem_gram = static_cast<size_t>(kJP) * kTilePitch * sizeof(double);
+  const size_t smem_eig = static_cast<size_t>(2) * kJP * kEigPitch * sizeof(double);
+  const size_t smem_apply = (static_cast<size_t>(kJP) * kTilePitch + static_cast<size_t>(kJP) * kWPitch) * sizeof(double);
+  if (!attr_set) {
+    SPE_CUDA(cudaFuncSetAttribute(k_jgram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gram));
+    SPE_CUDA(cudaFuncSetAttribute(k_jeig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eig));
+    SPE_CUDA(cudaFuncSetAttribute(k_japply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_apply));
+    attr_set = true;
+  }
+  k_jgram<<<dim3(npanels, jw.nsplit), 256, smem_gram, st>>>(X, mp, ld, col0, jw.nsplit, jw.gram_part);
+  SPE_CUDA(cudaGetLastError());
+  k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax);
+  SPE_CUDA(cudaGetLastError());
+  k_japply<<<dim3(npanels, static_cast<unsigned>(mp / kJRows), 2), 256, smem_apply, st>>>(X, W, ld, col0, jw.wp);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(3);
+  return SPEIGEN_OK;
+}
+
+int launch_cm_coldots(const double* A, const double* B, int64_t rows, int64_t cols, int64_t ld, double* out, cudaStream_t st) {
+  if (cols <= 0) return SPEIGEN_OK;
+  k_cm_coldots<<<static_cast<unsigned>(cols), kCT, 0, st>>>(A, B, rows, ld, out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_colabsmin(const double* A, int64_t rows, int64_t cols, int64_t ld, double* out, cudaStream_t st) {
+  if (cols <= 0) return SPEIGEN_OK;
+  k_cm_colabsmin<<<static_cast<unsigned>(cols), kCT, 0, st>>>(A, rows, ld, out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_penalty(const double* A, int64_t rows, int64_t cols, int64_t ld, StageConsts sc, double* out, cudaStream_t st) {
+  if (cols <= 0) return SPEIGEN_OK;
+  k_cm_penalty<<<static_cast<unsigned>(cols), kCT, 0, st>>>(A, rows, ld, sc, out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_scale_cols(double* A, int64_t rows, int64_t cols, int64_t ld, const double* s, int inv, cudaStream_t st) {
+  k_cm_scale_cols<<<grid2(rows, cols), 256, 0, st>>>(A, rows, cols, ld, s, inv);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_gather_cols(const double* In, int64_t rows, int64_t cols, int64_t ld, const int* perm, double* Out, cudaStream_t st) {
+  k_cm_gather_cols<<<grid2(rows, cols), 256, 0, st>>>(In, rows, ld, perm, Out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_pad_copy(const double* Src, int64_t m, int64_t lds, double* Dst, int64_t mp, int64_t ld, double shift,
+                       double pad_diag, cudaStream_t st) {
+  k_cm_pad_copy<<<grid2(mp, mp), 256, 0, st>>>(Src, m, lds, Dst, mp, ld, shift, pad_diag);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_identity(double* A, int64_t mp, int64_t ld, cudaStream_t st) {
+  k_cm_pad_copy<<<grid2(mp, mp), 256, 0, st>>>(nullptr, 0, 0, A, mp, ld, 0.0, 1.0);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_build_target(const double* V, const double* T, const double* inv_xi, const double* rho, const double* absmin,
+                           int q, StageConsts sc, int64_t m, int64_t mp, int64_t ld, double* B, cudaStream_t st) {
+  k_cm_build_target<<<grid2(mp, mp), 256, 0, st>>>(V, T, inv_xi, rho, absmin, q, sc, m, mp, ld, B);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_ns_matrix(const double* G, int64_t mp, int64_t ld, double* M, cudaStream_t st) {
+  k_cm_ns_matrix<<<grid2(mp, mp), 256, 0, st>>>(G, mp, ld, M);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_thres_norms(const double* V, int64_t m, int64_t ld, double thres, double* nrm2, cudaStream_t st) {
+  k_cm_thres_norms<<<static_cast<unsigned>(m), kCT, 0, st>>>(V, m, ld, thres, nrm2);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_thres_scale(const double* V, int64_t m, int64_t ld, double thres, const double* rs, const double* cs,
+                          double* Out, int64_t ldo, cudaStream_t st) {
+  k_cm_thres_scale<<<grid2(m, m), 256, 0, st>>>(V, m, ld, thres, rs, cs, Out, ldo);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_scan_sym(const double* S, int64_t m, int64_t ld, double* part, double* out4, cudaStream_t st) {
+  k_cm_scan_sym<<<static_cast<unsigned>(m), kCT, 0, st>>>(S, m, ld, part);
+  SPE_CUDA(cudaGetLastError());
+  k_cm_sum4<<<1, kCT, 0, st>>>(part, m, out4);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(2);
+  return SPEIGEN_OK;
+}
+int launch_cm_colsums(const double* X, int64_t n, int64_t m, int64_t ld, double* out, cudaStream_t st) {
+  k_cm_colsums<<<static_cast<unsigned>(m), kCT, 0, st>>>(X, n, ld, out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_cm_center(double* X, int64_t n, int64_t m, int64_t ld, const double* sums, double inv_n, cudaStream_t st) {
+  k_cm_center<<<grid2(n, m), 256, 0, st>>>(X, n, ld, sums, inv_n);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+
+}  // namespace speigen
