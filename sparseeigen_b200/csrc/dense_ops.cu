@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) k_jgram(const double* X, int64_t mp, int6
 // Two-sided cyclic Jacobi (round-robin parallel ordering, one warp per pair) on the 64 x 64 panel Gram matrix.
 // Writes the accumulated rotation with the two 32-column blocks exchanged (odd-even block ordering).
 constexpr int kEigPitch = kJP + 1;   // 65
-__global__ void __launch_bounds__(1024) k_jeig(const double* gram_part, int nsplit, double* wp, double* offmax) {
+__global__ void __launch_bounds__(1024) k_jeig(const double* gram_part, int nsplit, double* wp, double* offmax, int max_inner) {
   extern __shared__ __align__(16) double sm_dyn[];
   double* G = sm_dyn;                          // [64][65]
   double* W = sm_dyn + kJP * kEigPitch;        // [64][65]
@@ -363,46 +363,75 @@ __global__ void __launch_bounds__(1024) k_jeig(const double* gram_part, int nspl
   __syncthreads();
   const double panel_off = s_red[0];
   const double eps = 2.220446049250313e-16;
+  // Round-robin (circle method) pairing of the 64 indices: round r, slot w -> pair (p < q), tabulated once.
+  __shared__ unsigned char s_pp[(kJP - 1) * (kJP / 2)], s_qq[(kJP - 1) * (kJP / 2)];
+  for (int idx = threadIdx.x; idx < (kJP - 1) * (kJP / 2); idx += blockDim.x) {
+    const int r = idx / (kJP / 2), w = idx - r * (kJP / 2);
+    int a, b;
+    if (w == 0) { a = kJP - 1; b = r; }
+    else { a = (r + w) % (kJP - 1); b = (r - w + (kJP - 1)) % (kJP - 1); }
+    s_pp[idx] = static_cast<unsigned char>(min(a, b));
+    s_qq[idx] = static_cast<unsigned char>(max(a, b));
+  }
+  __syncthreads();
+  auto pair_of = [&](int r, int w, int& pi, int& qi) {
+    pi = s_pp[r * (kJP / 2) + w];
+    qi = s_qq[r * (kJP / 2) + w];
+  };
+  __shared__ double s_c[kJP / 2], s_s[kJP / 2];
   if (panel_off > eps) {
-    for (int sweep = 0; sweep < 60; ++sweep) {
+    const int ti = threadIdx.x >> 5;   // pair slot i (rows of the 2 x 2 block), warp-uniform
+    const int tj = threadIdx.x & 31;   // pair slot j (columns of the 2 x 2 block)
+    for (int sweep = 0; sweep < max_inner; ++sweep) {
       int any = 0;
       for (int r = 0; r < kJP - 1; ++r) {
-        int a, b;
-        if (warp == 0) { a = kJP - 1; b = r; }
-        else { a = (r + warp) % (kJP - 1); b = (r - warp + (kJP - 1)) % (kJP - 1); }
-        const int pi = min(a, b), qi = max(a, b);
-        // (pi,pi), (qi,qi), (pi,qi) are written only by this warp in this round -> no barrier needed before reading
-        const double gpp = G[pi * kEigPitch + pi], gqq = G[qi * kEigPitch + qi], gpq = G[pi * kEigPitch + qi];
-        double c = 1.0, s = 0.0;
-        const bool rot = fabs(gpq) > eps * sqrt(fabs(gpp) * fabs(gqq));
-        if (rot) {
-          const double zeta = (gqq - gpp) / (2.0 * gpq);
-          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          c = 1.0 / sqrt(1.0 + tt * tt);
-          s = c * tt;
-          any = 1;
-        }
-        // column phase: columns pi, qi of G and W
-        if (rot) {
-          for (int i = lane; i < kJP; i += 32) {
-            const double g1 = G[i * kEigPitch + pi], g2 = G[i * kEigPitch + qi];
-            G[i * kEigPitch + pi] = c * g1 - s * g2;
-            G[i * kEigPitch + qi] = s * g1 + c * g2;
-            const double w1 = W[i * kEigPitch + pi], w2 = W[i * kEigPitch + qi];
-            W[i * kEigPitch + pi] = c * w1 - s * w2;
-            W[i * kEigPitch + qi] = s * w1 + c * w2;
+        // phase 0: warp 0 computes the 32 rotations of this round (one pair per lane)
+        if (warp == 0) {
+          int pi, qi;
+          pair_of(r, lane, pi, qi);
+          const double gpp = G[pi * kEigPitch + pi], gqq = G[qi * kEigPitch + qi], gpq = G[pi * kEigPitch + qi];
+          double c = 1.0, sn = 0.0;
+          if (fabs(gpq) > eps * sqrt(fabs(gpp) * fabs(gqq))) {
+            // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (gqq - gpp) / (2 gpq), written with one sqrt and one division
+            const double a = gqq - gpp, b = 2.0 * gpq;
+            const double rr = sqrt(fma(a, a, b * b));
+            const double tt = b / (a + (a >= 0.0 ? rr : -rr));
+            c = rsqrt(fma(tt, tt, 1.0));
+            sn = c * tt;
+            any = 1;
           }
+          s_c[lane] = c;
+          s_s[lane] = sn;
         }
         __syncthreads();
-        // row phase: rows pi, qi of G
-        if (rot) {
-          for (int j = lane; j < kJP; j += 32) {
-            const double g1 = G[pi * kEigPitch + j], g2 = G[qi * kEigPitch + j];
-            G[pi * kEigPitch + j] = c * g1 - s * g2;
-            G[qi * kEigPitch + j] = s * g1 + c * g2;
+        // phase 1: G' = J^T G J as 32 x 32 independent 2 x 2 blocks (one per thread); W' = W J (two rows per thread)
+        {
+          int pi, qi, pj, qj;
+          pair_of(r, ti, pi, qi);
+          pair_of(r, tj, pj, qj);
+          const double ci = s_c[ti], si = s_s[ti], cj = s_c[tj], sj = s_s[tj];
+          if (si != 0.0 || sj != 0.0) {
+            const double g00 = G[pi * kEigPitch + pj], g01 = G[pi * kEigPitch + qj];
+            const double g10 = G[qi * kEigPitch + pj], g11 = G[qi * kEigPitch + qj];
+            // rows: [r0; r1] = R_i^T [g0.; g1.],  R = [[c, s], [-s, c]]
+            const double r00 = ci * g00 - si * g10, r01 = ci * g01 - si * g11;
+            const double r10 = si * g00 + ci * g10, r11 = si * g01 + ci * g11;
+            // columns: [.0 .1] R_j
+            double n00 = cj * r00 - sj * r01, n01 = sj * r00 + cj * r01;
+            double n10 = cj * r10 - sj * r11, n11 = sj * r10 + cj * r11;
+            if (ti == tj) { n01 = 0.0; n10 = 0.0; }      // the annihilated pair
+            G[pi * kEigPitch + pj] = n00; G[pi * kEigPitch + qj] = n01;
+            G[qi * kEigPitch + pj] = n10; G[qi * kEigPitch + qj] = n11;
           }
-          __syncwarp();
-          if (lane == 0) { G[pi * kEigPitch + qi] = 0.0; G[qi * kEigPitch + pi] = 0.0; }
+          if (sj != 0.0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int row = ti * 2 + h;
+              const double w1 = W[row * kEigPitch + pj], w2 = W[row * kEigPitch + qj];
+              W[row * kEigPitch + pj] = cj * w1 - sj * w2;
+              W[row * kEigPitch + qj] = sj * w1 + cj * w2;
+            }
+          }
         }
         __syncthreads();
       }
@@ -689,7 +718,7 @@ int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity
   }
   k_jgram<<<dim3(npanels, jw.nsplit), 256, smem_gram, st>>>(X, mp, ld, col0, jw.nsplit, jw.gram_part);
   SPE_CUDA(cudaGetLastError());
-  k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax);
+  k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, jw.inner_sweeps == 0 ? 60 : (jw.inner_sweeps < 0 ? 0 : jw.inner_sweeps));
   SPE_CUDA(cudaGetLastError());
   k_japply<<<dim3(npanels, static_cast<unsigned>(mp / kJRows), 2), 256, smem_apply, st>>>(X, W, ld, col0, jw.wp);
   SPE_CUDA(cudaGetLastError());

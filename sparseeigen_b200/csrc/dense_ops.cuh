@@ -37,6 +37,7 @@ struct JacobiWork {
   double* wp = nullptr;             // [max_panels][kJP*kJP] rotation of each panel (column-major, block swap folded in)
   double* offmax = nullptr;         // device scalar: max relative off-diagonal seen since the last reset
   int nsplit = 1;
+  int inner_sweeps = 0;             // cap on the 64 x 64 Jacobi sweeps per panel visit (0 = run to convergence)
 };
 // One round of the odd-even block ordering on X (mp x mp, ld) and the accumulated right factor W (same shape):
 // parity 0 pairs blocks (0,1),(2,3),..; parity 1 pairs (1,2),(3,4),...
