@@ -276,11 +276,20 @@ def run_loop(prob: Problem, thres=1e-9, keep_iterates=False, max_iter=MAX_ITER):
                 if rel_change <= tol[ee] or k >= max_iter:
                     break
             flg = 0
+    return finalize(V, thres), tr
+
+
+def finalize(V, thres):
+    """Threshold and "normalise", R/spEigen.R:158-160."""
     Vout = V.copy()
     Vout[np.abs(Vout) < thres] = 0                           # :158 (strict <)
     nrm = 1.0 / np.sqrt(np.sum(np.abs(Vout) ** 2, axis=0))   # :159
-    Vout = Vout * nrm[None, :]                               # :160
-    return Vout, tr
+    # :160 is `matrix(rep(nrm, m), ncol = q) * V`: rep() cycles the q factors through the column-major layout, so entry
+    # (i, j) is scaled by nrm[(i + j*m) mod q] -- what R computes, not a per-column normalisation (they coincide to
+    # ~1e-14 at the default thres, where every factor is 1 + O(m * thres^2)).
+    mm, qq = Vout.shape
+    lin = np.arange(mm)[:, None] + mm * np.arange(qq)[None, :]
+    return Vout * nrm[lin % qq]                              # :160
 
 
 def spEigen(X, q=1, rho=0.5, data=False, d=None, V=None, thres=1e-9, mode="reference",

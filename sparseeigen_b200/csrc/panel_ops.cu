@@ -454,11 +454,16 @@ __global__ void __launch_bounds__(kPT) k_thres_norms(const double* V, int64_t m,
   }
 }
 
+// R/spEigen.R:160 is `matrix(rep(nrm, m), ncol = q) * V`: rep() cycles the q factors through the column-major m x q
+// layout, so entry (r, c) is scaled by nrm[(r + c m) mod q] (NOT by its own column's factor unless q == 1).  With the
+// default thres the factors differ from 1 by ~1e-14 and the difference is invisible; with a large thres it is not.
+// The drop-in reproduces what the reference computes.
 template <bool CPLX>
-__global__ void k_thres_scale_colmajor(const double* V, int64_t m, int q, int pitch, double thres, const double* nrm,
+__global__ void k_thres_scale_colmajor(const double* V, int64_t m, int q, int pitch, double thres, const double* nrm_by_col,
                                        double* out) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= m * q) return;
+  const double* nrm = nrm_by_col + (idx % q) - (idx / m);   // so that nrm[c] below reads nrm_by_col[idx mod q]
   const int c = static_cast<int>(idx / m);
   const int64_t r = idx - static_cast<int64_t>(c) * m;
   const double* row = V + r * pitch;

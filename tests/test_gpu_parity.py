@@ -225,6 +225,16 @@ def test_e2e_custom_d_V_thres_q1():
     assert r["vectors"].shape == (300, 1) and abs(np.linalg.norm(r["vectors"]) - 1) < 1e-12
     big = sb.spEigen(S, 4, thres=0.05)
     assert np.all((np.abs(big["vectors"]) == 0) | (np.abs(big["vectors"]) >= 0.05 * 0.99))
+    # R/spEigen.R:160 `matrix(rep(nrm, m), ncol = q) * V` cycles the q factors through the column-major layout: when the
+    # threshold removes real mass, entries are NOT scaled by their own column's factor.  Same iterate in (the solver is
+    # bit-reproducible; thres = 0 returns the un-thresholded iterate), same quirk out.
+    V = sb.spEigen(S, 4, thres=0.0)["vectors"]
+    cut = sb.spEigen(S, 4, thres=0.17)["vectors"]
+    want = o.finalize(V, 0.17)
+    assert np.array_equal(cut != 0, want != 0) and 4 < np.count_nonzero(cut) < np.count_nonzero(V)
+    assert np.max(np.abs(cut - want)) < 1e-12
+    Vt = np.where(np.abs(V) < 0.17, 0.0, V)
+    assert np.max(np.abs(want - Vt / np.linalg.norm(Vt, axis=0)[None, :])) > 1e-3     # the quirk is visible here
 
 
 @pytest.mark.parametrize("name", ["real_cov", "real_data", "cplx_cov", "cplx_data"])
