@@ -1,0 +1,12 @@
+/* Declaration-only stand-in for <R_ext/Rdynload.h> (see ../R.h). */
+#ifndef STUB_RDYNLOAD_H
+#define STUB_RDYNLOAD_H
+typedef void* (*DL_FUNC)(void);
+typedef struct { const char* name; DL_FUNC fun; int numArgs; } R_CallMethodDef;
+typedef struct _DllInfo DllInfo;
+typedef int Rboolean;
+#define FALSE 0
+#define TRUE 1
+int R_registerRoutines(DllInfo*, const void*, const R_CallMethodDef*, const void*, const void*);
+Rboolean R_useDynamicSymbols(DllInfo*, Rboolean);
+#endif

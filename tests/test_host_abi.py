@@ -32,11 +32,45 @@ def test_library_exports_every_declared_symbol():
 def test_r_glue_uses_only_exported_symbols():
     """integration/r-package/src/speigen_glue.c (the .Call stub of INTEGRATION.md) binds only exported ABI symbols."""
     src = open(os.path.join(ROOT, "integration", "r-package", "src", "speigen_glue.c")).read()
-    used = set(re.findall(r"\b(speigen_(?:run_f64|run_c64|cfg_default|last_error|shutdown))\s*\(", src))
-    assert {"speigen_run_f64", "speigen_run_c64", "speigen_cfg_default", "speigen_last_error", "speigen_shutdown"} <= used
+    used = set(re.findall(r"\b(speigen(?:cov)?_(?:run_f64|run_c64|run_cov_of_data_f64|cfg_default|last_error|shutdown))\s*\(", src))
+    assert {"speigen_run_f64", "speigen_run_c64", "speigen_cfg_default", "speigen_last_error", "speigen_shutdown",
+            "speigencov_run_f64", "speigencov_cfg_default", "speigen_run_cov_of_data_f64"} <= used
     L = sb.lib()
     for s in used:
         assert hasattr(L, s)
+
+
+def test_r_glue_type_checks_against_the_header():
+    """`gcc -fsyntax-only` of the .Call glue against include/speigen_b200.h and declaration-only stand-ins for the R
+    headers (tests/stubs/r_headers; R itself is not installed in the image): argument counts and types of every ABI call
+    the glue makes are checked by the compiler."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "stubs", "r_headers"),
+                        "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "integration", "r-package", "src", "speigen_glue.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_header_compiles_as_plain_c():
+    """include/speigen_b200.h is a C header (no C++/torch types in any signature)."""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write('#include "speigen_b200.h"\nint main(void) { speigen_cfg c; speigencov_cfg d; (void)c; (void)d; return 0; }\n')
+        path = f.name
+    try:
+        r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I",
+                            os.path.join(ROOT, "include"), path], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    finally:
+        os.unlink(path)
 
 
 def test_struct_layouts_match_the_header():
