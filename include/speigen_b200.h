@@ -189,8 +189,8 @@ int speigen_solver_stream(speigen_solver* s, int32_t local_idx, void** cuda_stre
 
 /* ==== SURVEY §8(f)-1: spEigenCov(S, q = 1, rho = 0.5, thres = 1e-9)                     R/spEigenCov.R:48 ========
  * returning list(vectors = m x m, values = m, cov = m x m)                                R/spEigenCov.R:135
- * Joint estimation of sparse eigenvectors and eigenvalues.  Real FP64 in this build (complex S returns
- * SPEIGEN_ERR_UNSUPPORTED).  Additional status codes mirror its own stop() conditions. */
+ * Joint estimation of sparse eigenvectors and eigenvalues, real or complex Hermitian S (complex matrices run through the
+ * same real kernels in embedded form [[Sr, -Si], [Si, Sr]]).  Additional status codes mirror its own stop() conditions. */
 #define SPEIGEN_ERR_Q_GT_M 8          /* "q should not be larger than m."               R/spEigenCov.R:55 */
 #define SPEIGEN_ERR_NOT_PSD 9         /* "The covariance matrix is not PSD."           R/spEigenCov.R:63 */
 #define SPEIGEN_ERR_LOW_RANK 10       /* "The covariance matrix is low-rank."          R/spEigenCov.R:65 */
@@ -235,6 +235,9 @@ typedef struct speigencov_out {
 
 /* one-shot drop-in call (host pointers): S is m x m column-major */
 int speigencov_run_f64(const double* S, int64_t nrow, int64_t ncol, double q, double rho, double thres,
+                       const speigencov_cfg* cfg, speigencov_out* out);
+/* complex Hermitian S, interleaved {re, im}; vectors / cov are 2*m*m doubles (interleaved), values m doubles */
+int speigencov_run_c64(const double* S_interleaved, int64_t nrow, int64_t ncol, double q, double rho, double thres,
                        const speigencov_cfg* cfg, speigencov_out* out);
 /* R/spEigenCov.R:52-60 without the matrix scans (host only) */
 int speigencov_validate_args(int64_t nrow, int64_t ncol, double q, double rho);

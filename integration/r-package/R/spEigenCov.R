@@ -11,8 +11,7 @@ spEigenCov <- function(S, q = 1, rho = 0.5, thres = 1e-9) {
   if (!isSymmetric.matrix(S)) stop("The covariance matrix is not symmetric")                 # :57
   if ((q %% 1) != 0 || q <= 0) stop("The input argument q should be a positive integer.")    # :58
   if (rho <= 0) stop("The input argument rho should be positive.")                           # :59
-  if (is.complex(S)) stop("spEigenCov: complex S is not supported by the B200 build yet")
-  storage.mode(S) <- "double"
+  if (!is.complex(S)) storage.mode(S) <- "double"
   # "not PSD" (:63) and "low-rank" (:65) are raised by the library from the device eigen-decomposition
   .Call(C_speigencov_call, S, as.double(q), as.double(rho), as.double(thres),
         as.integer(getOption("sparseEigen.device", 0L)))

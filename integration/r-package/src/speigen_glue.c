@@ -51,19 +51,20 @@ SEXP speigen_call(SEXP X, SEXP q, SEXP rho, SEXP data, SEXP d, SEXP V, SEXP thre
 SEXP speigencov_call(SEXP S, SEXP q, SEXP rho, SEXP thres, SEXP device) {
   SEXP dim = getAttrib(S, R_DimSymbol);
   const int64_t nrow = INTEGER(dim)[0], ncol = INTEGER(dim)[1];
-  if (isComplex(S)) Rf_error("spEigenCov: complex S is not supported by the B200 build yet");
+  const int cplx = isComplex(S);
   speigencov_cfg cfg;
   speigencov_cfg_default(&cfg);
   cfg.device = asInteger(device);
   speigencov_out out;
   memset(&out, 0, sizeof(out));
-  SEXP vec = PROTECT(allocMatrix(REALSXP, (int)ncol, (int)ncol));
+  SEXP vec = PROTECT(allocMatrix(cplx ? CPLXSXP : REALSXP, (int)ncol, (int)ncol));
   SEXP val = PROTECT(allocVector(REALSXP, (R_xlen_t)ncol));
-  SEXP cov = PROTECT(allocMatrix(REALSXP, (int)ncol, (int)ncol));
-  out.vectors = REAL(vec);
+  SEXP cov = PROTECT(allocMatrix(cplx ? CPLXSXP : REALSXP, (int)ncol, (int)ncol));
+  out.vectors = cplx ? (double*)COMPLEX(vec) : REAL(vec);            /* Rcomplex = {double r, i} = interleaved */
   out.values = REAL(val);
-  out.cov = REAL(cov);
-  const int rc = speigencov_run_f64(REAL(S), nrow, ncol, asReal(q), asReal(rho), asReal(thres), &cfg, &out);
+  out.cov = cplx ? (double*)COMPLEX(cov) : REAL(cov);
+  const int rc = cplx ? speigencov_run_c64((const double*)COMPLEX(S), nrow, ncol, asReal(q), asReal(rho), asReal(thres), &cfg, &out)
+                      : speigencov_run_f64(REAL(S), nrow, ncol, asReal(q), asReal(rho), asReal(thres), &cfg, &out);
   if (rc != SPEIGEN_OK) {
     UNPROTECT(3);
     Rf_error("%s", speigen_last_error());

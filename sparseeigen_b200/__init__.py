@@ -143,6 +143,7 @@ def lib():
     L.speigencov_cfg_default.argtypes = [C.POINTER(CovCfg)]
     L.speigencov_run_f64.argtypes = [_dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.POINTER(CovCfg),
                                      C.POINTER(CovOut)]
+    L.speigencov_run_c64.argtypes = L.speigencov_run_f64.argtypes
     L.speigencov_validate_args.argtypes = [C.c_int64, C.c_int64, C.c_double, C.c_double]
     L.speigencov_schedule.argtypes = [C.POINTER(CovCfg), _dp, _dp, _dp]
     L.speigencov_eigval_algo.argtypes = [_dp, C.c_int64, C.c_double, C.c_int32, C.c_int32, _dp]
@@ -369,7 +370,7 @@ def spEigenCov(S, q=1, rho=0.5, thres=1e-9, *, cfg: Optional[CovCfg] = None, wan
     """Covariance estimation with sparse eigenvectors — drop-in for R/spEigenCov.R:48.
 
     Returns dict(vectors m x m, values m, cov m x m) as the reference's list (R/spEigenCov.R:135) plus an 'info' side
-    channel (objective trajectory, sweep counts, timings).  Real S in this build."""
+    channel (objective trajectory, sweep counts, timings).  Real or complex Hermitian S."""
     S = np.asarray(S)
     if S.ndim == 0:
         S = S.reshape(1, 1)
@@ -382,18 +383,18 @@ def spEigenCov(S, q=1, rho=0.5, thres=1e-9, *, cfg: Optional[CovCfg] = None, wan
     qq = float("nan") if _is_na(q) else float(q)
     rr = float("nan") if _is_na(rho) else float(rho)
     _check(L.speigencov_validate_args(nrow, m, qq, rr))                               # :54-60
-    if np.iscomplexobj(S):
-        raise SpEigenError(25, "complex S is not supported by spEigenCov in this build")
-    Sf = _as_colmajor(S, False)
+    cplx = np.iscomplexobj(S)
+    Sf = _as_colmajor(S, cplx)
     cfg = cfg or default_cov_cfg()
     for k, v in cfg_overrides.items():
         if not hasattr(cfg, k):
             raise TypeError(f"unknown cfg field {k}")
         setattr(cfg, k, v)
     cap = max(cfg.max_iter, 1)
-    vectors = np.zeros((m, m), order="F")
+    dt = np.complex128 if cplx else np.float64
+    vectors = np.zeros((m, m), dtype=dt, order="F")
     values = np.zeros(m)
-    covm = np.zeros((m, m), order="F") if want_cov else None
+    covm = np.zeros((m, m), dtype=dt, order="F") if want_cov else None
     F = np.zeros(cap)
     stage = np.zeros(cap, dtype=np.int32)
     o = CovOut()
@@ -403,7 +404,8 @@ def spEigenCov(S, q=1, rho=0.5, thres=1e-9, *, cfg: Optional[CovCfg] = None, wan
     o.F = _ptr(F)
     o.stage_of_k = stage.ctypes.data_as(C.POINTER(C.c_int32))
     o.trace_capacity = cap
-    _check(L.speigencov_run_f64(Sf.ctypes.data_as(_dp), nrow, m, qq, rr, float(thres), C.byref(cfg), C.byref(o)))
+    fn = L.speigencov_run_c64 if cplx else L.speigencov_run_f64
+    _check(fn(Sf.ctypes.data_as(_dp), nrow, m, qq, rr, float(thres), C.byref(cfg), C.byref(o)))
     k = min(o.iterations, cap)
     info = dict(iterations=o.iterations, eig_sweeps=o.eig_sweeps, svd_sweeps=o.svd_sweeps, gemms=o.gemms,
                 seconds_upload=o.seconds_upload, seconds_init=o.seconds_init, seconds_loop=o.seconds_loop,

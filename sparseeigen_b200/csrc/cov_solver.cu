@@ -382,17 +382,69 @@ struct DenseCtx {
     SPE_CUDA(cudaMemcpyAsync(V, X, static_cast<size_t>(mp) * ld * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return sync();
   }
+  // eigen(S) for a Hermitian S carried in embedded form (dimension mp = 2h): every eigenvalue of S appears twice in the
+  // embedding, with real eigenvectors [x; y] and [-y; x] that are the same complex vector x + i y up to the phase i.
+  // After sorting, one vector of each adjacent pair is kept.  X = embed(S) zero-padded (destroyed); V receives the
+  // embedded, sorted, re-orthonormalised eigenvector matrix.
+  int eigh_embedded(double* X, double* W, double* V, int64_t mc, int64_t h, std::vector<double>& lam, int* sweeps_out) {
+    SPE_TRY2(jacobi(X, W, sweeps_out));
+    SPE_TRY2(launch_cm_coldots(W, X, mp, mp, ld, vec[0], st));
+    SPE_TRY2(launch_cm_coldots(W, W, mp, mp, ld, vec[1], st));
+    double* hq = h_pinned;
+    double* hn = h_pinned + mp;
+    SPE_CUDA(cudaMemcpyAsync(hq, vec[0], mp * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SPE_CUDA(cudaMemcpyAsync(hn, vec[1], mp * sizeof(double), cudaMemcpyDeviceToHost, st));
+    // mass of each real eigenvector inside the un-padded coordinates (rows [0, mc) and [h, h + mc))
+    SPE_TRY2(launch_cm_coldots(W, W, mc, mp, ld, vec[0], st));
+    SPE_TRY2(launch_cm_coldots(W + h, W + h, mc, mp, ld, vec[1], st));
+    double* hm0 = h_pinned + 2 * mp;
+    double* hm1 = h_pinned + 3 * mp;
+    SPE_CUDA(cudaMemcpyAsync(hm0, vec[0], mp * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SPE_CUDA(cudaMemcpyAsync(hm1, vec[1], mp * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SPE_TRY2(sync());
+    for (int64_t j = 0; j < mp; ++j)
+      if (hn[j] > 0.0) hq[j] /= hn[j];
+    std::vector<int> order(mp);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      const bool pa = (hm0[a] + hm1[a]) < 0.5 * hn[a], pb = (hm0[b] + hm1[b]) < 0.5 * hn[b];
+      if (pa != pb) return pb;
+      return hq[a] > hq[b];
+    });
+    lam.resize(mc);
+    std::vector<int> pick(mp, 0);
+    const double scale = std::fabs(hq[order[0]]);
+    for (int64_t k = 0; k < mc; ++k) {
+      const double l0 = hq[order[2 * k]], l1 = hq[order[2 * k + 1]];
+      if (std::fabs(l0 - l1) > 1e-9 * scale) {
+        set_error("complex eigen-decomposition: eigenvalue pair %lld of the embedded matrix does not match (%.17g vs %.17g)",
+                  (long long)k, l0, l1);
+        return SPEIGEN_ERR_CUDA;
+      }
+      lam[k] = 0.5 * (l0 + l1);
+      pick[k] = order[2 * k];
+    }
+    SPE_CUDA(cudaMemcpyAsync(perm, pick.data(), static_cast<size_t>(mp) * sizeof(int), cudaMemcpyHostToDevice, st));
+    SPE_TRY2(launch_ce_select_eigvecs(W, perm, mc, h, ld, V, st));
+    SPE_TRY2(gemm(mp, mp, mp, V, 1, V, 1, X, 1.0, 1));
+    SPE_TRY2(launch_cm_ns_matrix(X, mp, ld, W, st));
+    SPE_TRY2(gemm(mp, mp, mp, V, 0, W, 1, X));
+    SPE_CUDA(cudaMemcpyAsync(V, X, static_cast<size_t>(mp) * ld * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return sync();
+  }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // spEigenCov driver
 // ---------------------------------------------------------------------------------------------------------------
+// cplx: S_host is interleaved {re, im}; every m x m matrix is carried in real embedded form of dimension 2h (dense_ops.cuh)
 static int run_speigencov(const double* S_host, int64_t m, int q, double rho, double thres, const speigencov_cfg& cfg,
-                          speigencov_out* out) {
+                          speigencov_out* out, bool cplx) {
   DenseCtx cx;
   const double t_start = now_s();
-  // matrices: 0 S_hat, 1 V, 2 T, 3 X (Jacobi work / target), 4 W, 5 tmp, 6 raw S (m x m in an mp x ld buffer)
-  int rc = cx.create(cfg.device, m, 7);
+  const int64_t h = cplx ? round_up(m, 64) : 0;
+  // matrices: 0 S_hat, 1 V, 2 T, 3 X (Jacobi work / target), 4 W, 5 tmp, 6 raw S (m x m in an mp x ld buffer; complex: flat)
+  int rc = cx.create(cfg.device, cplx ? 2 * h : m, 7);
   if (rc != SPEIGEN_OK) { cx.destroy(); return rc; }
   cx.max_sweeps = cfg.jacobi_max_sweeps > 0 ? cfg.jacobi_max_sweeps : 40;
   if (cfg.jacobi_tol > 0.0) cx.jtol = cfg.jacobi_tol;
@@ -401,15 +453,26 @@ static int run_speigencov(const double* S_host, int64_t m, int q, double rho, do
     double *Sh = cx.mats[0], *V = cx.mats[1], *T = cx.mats[2], *X = cx.mats[3], *W = cx.mats[4], *tmp = cx.mats[5],
            *Sraw = cx.mats[6];
     cudaStream_t st = cx.st;
-    SPE_CUDA(cudaMemcpy2DAsync(Sraw, ld * sizeof(double), S_host, m * sizeof(double), m * sizeof(double), m,
-                               cudaMemcpyHostToDevice, st));
+    const int64_t rows_v = cplx ? mp : m;   // rows that carry a column of V / T (embedded: real and imaginary halves)
+    if (cplx) {
+      SPE_CUDA(cudaMemcpyAsync(Sraw, S_host, static_cast<size_t>(2) * m * m * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+      SPE_CUDA(cudaMemcpy2DAsync(Sraw, ld * sizeof(double), S_host, m * sizeof(double), m * sizeof(double), m,
+                                 cudaMemcpyHostToDevice, st));
+    }
     SPE_TRY2(cx.sync());
     out->seconds_upload = now_s() - t_start;
     const double t_init = now_s();
     // anyNA / isSymmetric.matrix / ||S||_F                                                  R/spEigenCov.R:56-57,73
-    SPE_TRY2(launch_cm_scan_sym(Sraw, m, ld, cx.scan_part, cx.vec[2], st));
+    if (cplx) {   // the embedding of S is symmetric iff S is Hermitian; every sum below counts each entry twice
+      SPE_TRY2(launch_ce_embed(Sraw, m, X, h, ld, 0.0, 0.0, st));
+      SPE_TRY2(launch_cm_scan_sym(X, mp, ld, cx.scan_part, cx.vec[2], st));
+    } else {
+      SPE_TRY2(launch_cm_scan_sym(Sraw, m, ld, cx.scan_part, cx.vec[2], st));
+    }
     double sc4[4];
     SPE_TRY2(cx.d2h(sc4, cx.vec[2], 4));
+    if (cplx) sc4[3] *= 0.5;
     if (cfg.check_na && sc4[2] > 0.0) { set_error("This function cannot handle NAs."); return SPEIGEN_ERR_NA; }
     if (cfg.check_symmetric) {
       const double tol = 100.0 * 2.220446049250313e-16;
@@ -418,10 +481,14 @@ static int run_speigencov(const double* S_host, int64_t m, int q, double rho, do
     }
     const double fro = std::sqrt(sc4[3]);
     // eigen(S)                                                                               :62-68
-    SPE_TRY2(launch_cm_pad_copy(Sraw, m, ld, X, mp, ld, 0.0, 0.0, st));
     std::vector<double> Xi;
     int esw = 0;
-    SPE_TRY2(cx.eigh(X, W, V, Xi, &esw));
+    if (cplx) {
+      SPE_TRY2(cx.eigh_embedded(X, W, V, m, h, Xi, &esw));
+    } else {
+      SPE_TRY2(launch_cm_pad_copy(Sraw, m, ld, X, mp, ld, 0.0, 0.0, st));
+      SPE_TRY2(cx.eigh(X, W, V, Xi, &esw));
+    }
     out->eig_sweeps = esw;
     for (int64_t j = 0; j < m; ++j)
       if (Xi[j] <= cfg.psd_tol) { set_error("The covariance matrix is not PSD."); return SPEIGEN_ERR_NOT_PSD; }
@@ -433,7 +500,8 @@ static int run_speigencov(const double* S_host, int64_t m, int q, double rho, do
     if (rank < m) { set_error("The covariance matrix is low-rank."); return SPEIGEN_ERR_LOW_RANK; }
     const double xi_max = Xi[0];
     const double shift = xi_max + cfg.shift;                                                  // :69
-    SPE_TRY2(launch_cm_pad_copy(Sraw, m, ld, Sh, mp, ld, shift, 0.0, st));
+    if (cplx) SPE_TRY2(launch_ce_embed(Sraw, m, Sh, h, ld, shift, 0.0, st));
+    else SPE_TRY2(launch_cm_pad_copy(Sraw, m, ld, Sh, mp, ld, shift, 0.0, st));
     std::vector<double> rho_vec(q);
     for (int j = 0; j < q; ++j) rho_vec[j] = rho * cfg.rho_scale * fro * Xi[j] / Xi[0];       // :73
     double* d_rho = cx.vec[3];
@@ -448,8 +516,8 @@ static int run_speigencov(const double* S_host, int64_t m, int q, double rho, do
     std::vector<double> dots(m), vn(m), gq(q), inv_xi(mp, 0.0), F_v;
     auto refresh_T = [&]() -> int {
       SPE_TRY2(cx.gemm(mp, mp, mp, Sh, 1, V, 1, T));                                          // S_hat symmetric: S_hat^T V
-      SPE_TRY2(launch_cm_coldots(V, T, m, m, ld, d_dots, st));
-      SPE_TRY2(launch_cm_coldots(V, V, m, m, ld, d_vn, st));
+      SPE_TRY2(launch_cm_coldots(V, T, rows_v, m, ld, d_dots, st));                           // Re(v_j^H t_j)
+      SPE_TRY2(launch_cm_coldots(V, V, rows_v, m, ld, d_vn, st));
       double* h = cx.h_pinned;
       SPE_CUDA(cudaMemcpyAsync(h, d_dots, m * sizeof(double), cudaMemcpyDeviceToHost, st));
       SPE_CUDA(cudaMemcpyAsync(h + mp, d_vn, m * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -471,8 +539,13 @@ static int run_speigencov(const double* S_host, int64_t m, int q, double rho, do
         // eigenvector update: B = -(H1 + S_hat V diag(1/Xi)), V <- polar(B)                   :100-103,:146-160
         for (int64_t j = 0; j < m; ++j) inv_xi[j] = 1.0 / Xi[j];
         SPE_TRY2(cx.h2d(cx.vec[2], inv_xi.data(), mp));
-        SPE_TRY2(launch_cm_colabsmin(V, m, q, ld, cx.vec[1], st));
-        SPE_TRY2(launch_cm_build_target(V, T, cx.vec[2], d_rho, cx.vec[1], q, sc, m, mp, ld, X, st));
+        if (cplx) {
+          SPE_TRY2(launch_ce_colabsmin(V, m, h, q, ld, cx.vec[1], st));
+          SPE_TRY2(launch_ce_build_target(V, T, cx.vec[2], d_rho, cx.vec[1], q, sc, m, h, ld, X, st));
+        } else {
+          SPE_TRY2(launch_cm_colabsmin(V, m, q, ld, cx.vec[1], st));
+          SPE_TRY2(launch_cm_build_target(V, T, cx.vec[2], d_rho, cx.vec[1], q, sc, m, mp, ld, X, st));
+        }
         // eigenvalue update from the OLD A = V diag(1/Xi): g_j = -a_j^T S_hat a_j = -dots_j / Xi_j^2   :106-107
         for (int64_t j = 0; j < m; ++j) g[j] = -dots[j] * inv_xi[j] * inv_xi[j];
         SPE_TRY2(eigval_algo_host(g.data(), m, xi_max, q, 0, Xi_new.data()));
@@ -482,7 +555,8 @@ static int run_speigencov(const double* S_host, int64_t m, int q, double rho, do
         Xi = Xi_new;
         // objective                                                                          :110-114
         SPE_TRY2(refresh_T());
-        SPE_TRY2(launch_cm_penalty(V, m, q, ld, sc, cx.vec[1], st));
+        if (cplx) SPE_TRY2(launch_ce_penalty(V, m, h, q, ld, sc, cx.vec[1], st));
+        else SPE_TRY2(launch_cm_penalty(V, m, q, ld, sc, cx.vec[1], st));
         SPE_TRY2(cx.d2h(gq.data(), cx.vec[1], q));
         double F = 0.0;
         for (int64_t j = 0; j < m; ++j) F += std::log(Xi[j]);
@@ -506,21 +580,35 @@ static int run_speigencov(const double* S_host, int64_t m, int q, double rho, do
     out->svd_sweeps = svd_sweeps;
     out->seconds_loop = now_s() - t_loop;
     // threshold, the reference's row-wise normalisation, cov                                 :131-135
-    SPE_TRY2(launch_cm_thres_norms(V, m, ld, thres, cx.vec[0], st));
+    if (cplx) SPE_TRY2(launch_ce_thres_norms(V, m, h, ld, thres, cx.vec[0], st));
+    else SPE_TRY2(launch_cm_thres_norms(V, m, ld, thres, cx.vec[0], st));
     std::vector<double> nrm(m);
     SPE_TRY2(cx.d2h(nrm.data(), cx.vec[0], m));
     for (int64_t j = 0; j < m; ++j) nrm[j] = 1.0 / std::sqrt(nrm[j]);
     SPE_TRY2(cx.h2d(cx.vec[0], nrm.data(), m));
-    SPE_TRY2(launch_cm_thres_scale(V, m, ld, thres, cx.vec[0], nullptr, X, ld, st));          // row i scaled by nrm[i] (:133)
-    SPE_CUDA(cudaMemcpy2DAsync(out->vectors, m * sizeof(double), X, ld * sizeof(double), m * sizeof(double), m,
-                               cudaMemcpyDeviceToHost, st));
     std::memcpy(out->values, Xi.data(), m * sizeof(double));
-    if (out->cov) {
-      SPE_TRY2(cx.h2d(cx.vec[1], Xi.data(), m));
-      SPE_TRY2(launch_cm_thres_scale(X, m, ld, 0.0, nullptr, cx.vec[1], W, ld, st));          // Vout diag(Xi)
-      SPE_TRY2(cx.gemm(m, m, m, W, 0, X, 0, tmp));                                            // (Vout Xi) Vout^T
-      SPE_CUDA(cudaMemcpy2DAsync(out->cov, m * sizeof(double), tmp, ld * sizeof(double), m * sizeof(double), m,
+    if (cplx) {
+      SPE_TRY2(launch_ce_thres_scale(V, m, h, ld, thres, cx.vec[0], nullptr, X, st));         // row i scaled by nrm[i] (:133)
+      SPE_TRY2(launch_ce_extract(X, m, h, ld, Sraw, st));
+      SPE_CUDA(cudaMemcpyAsync(out->vectors, Sraw, static_cast<size_t>(2) * m * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (out->cov) {
+        SPE_TRY2(cx.h2d(cx.vec[1], Xi.data(), m));
+        SPE_TRY2(launch_ce_thres_scale(X, m, h, ld, 0.0, nullptr, cx.vec[1], W, st));         // embed(Vout diag(Xi))
+        SPE_TRY2(cx.gemm(mp, mp, mp, W, 0, X, 0, tmp));                                       // embed((Vout Xi) Vout^H)
+        SPE_TRY2(launch_ce_extract(tmp, m, h, ld, Sraw, st));
+        SPE_CUDA(cudaMemcpyAsync(out->cov, Sraw, static_cast<size_t>(2) * m * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+      }
+    } else {
+      SPE_TRY2(launch_cm_thres_scale(V, m, ld, thres, cx.vec[0], nullptr, X, ld, st));        // row i scaled by nrm[i] (:133)
+      SPE_CUDA(cudaMemcpy2DAsync(out->vectors, m * sizeof(double), X, ld * sizeof(double), m * sizeof(double), m,
                                  cudaMemcpyDeviceToHost, st));
+      if (out->cov) {
+        SPE_TRY2(cx.h2d(cx.vec[1], Xi.data(), m));
+        SPE_TRY2(launch_cm_thres_scale(X, m, ld, 0.0, nullptr, cx.vec[1], W, ld, st));        // Vout diag(Xi)
+        SPE_TRY2(cx.gemm(m, m, m, W, 0, X, 0, tmp));                                          // (Vout Xi) Vout^T
+        SPE_CUDA(cudaMemcpy2DAsync(out->cov, m * sizeof(double), tmp, ld * sizeof(double), m * sizeof(double), m,
+                                   cudaMemcpyDeviceToHost, st));
+      }
     }
     SPE_TRY2(cx.sync());
     out->gemms = cx.gemms;
@@ -620,7 +708,24 @@ int speigencov_run_f64(const double* S, int64_t nrow, int64_t ncol, double q, do
   }
   out->iterations = out->eig_sweeps = out->svd_sweeps = out->gemms = 0;
   out->seconds_upload = out->seconds_init = out->seconds_loop = out->seconds_gemm = 0.0;
-  return run_speigencov(S, ncol, static_cast<int>(q), rho, thres, cfg, out);
+  return run_speigencov(S, ncol, static_cast<int>(q), rho, thres, cfg, out, false);
+}
+
+int speigencov_run_c64(const double* S, int64_t nrow, int64_t ncol, double q, double rho, double thres,
+                       const speigencov_cfg* cfg_in, speigencov_out* out) {
+  DeviceRestoreCov restore__;
+  if (!S || !out || !out->vectors || !out->values) { set_error("null argument"); return SPEIGEN_ERR_ARG; }
+  speigencov_cfg cfg;
+  if (cfg_in) cfg = *cfg_in; else speigencov_cfg_default(&cfg);
+  int rc = speigencov_validate_args(nrow, ncol, q, rho);
+  if (rc != SPEIGEN_OK) return rc;
+  if (static_cast<int64_t>(q) >= ncol) {
+    set_error("spEigenCov with q == m is not supported (the reference's g[(q+1):m] runs backwards there)");
+    return SPEIGEN_ERR_UNSUPPORTED;
+  }
+  out->iterations = out->eig_sweeps = out->svd_sweeps = out->gemms = 0;
+  out->seconds_upload = out->seconds_init = out->seconds_loop = out->seconds_gemm = 0.0;
+  return run_speigencov(S, ncol, static_cast<int>(q), rho, thres, cfg, out, true);
 }
 
 // ---- dense kernel-level entry points --------------------------------------------------------------------------

@@ -663,6 +663,119 @@ __global__ void k_cm_center(double* X, int64_t n, int64_t ld, const double* sums
     X[j * ld + i] -= mu;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+//                          complex matrices in real embedded form [[Cr, -Ci], [Ci, Cr]]
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ce_store(double* D, int64_t ld, int64_t h, int64_t i, int64_t j, double re, double im) {
+  D[j * ld + i] = re;
+  D[j * ld + h + i] = im;
+  D[(h + j) * ld + i] = -im;
+  D[(h + j) * ld + h + i] = re;
+}
+__global__ void k_ce_embed(const double* Src, int64_t m, double* Dst, int64_t h, int64_t ld, double shift, double pad_diag) {
+  const int64_t j = blockIdx.y;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < h; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    double re = 0.0, im = 0.0;
+    if (i < m && j < m) {
+      re = Src[2 * (j * m + i)] - (i == j ? shift : 0.0);
+      im = Src[2 * (j * m + i) + 1];
+    } else if (i == j) {
+      re = pad_diag;
+    }
+    ce_store(Dst, ld, h, i, j, re, im);
+  }
+}
+__global__ void k_ce_select_eigvecs(const double* W, const int* perm, int64_t m, int64_t h, int64_t ld, double* V) {
+  const int64_t j = blockIdx.y;
+  const int64_t src = j < m ? perm[j] : 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < h; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    double re, im;
+    if (j < m) { re = W[src * ld + i]; im = W[src * ld + h + i]; }
+    else { re = (i == j) ? 1.0 : 0.0; im = 0.0; }
+    ce_store(V, ld, h, i, j, re, im);
+  }
+}
+__global__ void __launch_bounds__(kCT) k_ce_colabsmin(const double* V, int64_t m, int64_t h, int64_t ld, double* out) {
+  __shared__ double red[kCT / 32];
+  const int64_t j = blockIdx.x;
+  double s = 1.0e300;
+  for (int64_t i = threadIdx.x; i < m; i += kCT) s = fmin(s, hypot(V[j * ld + i], V[j * ld + h + i]));
+  s = block_min(s, red);
+  if (threadIdx.x == 0) out[j] = s;
+}
+__global__ void __launch_bounds__(kCT) k_ce_penalty(const double* V, int64_t m, int64_t h, int64_t ld, StageConsts sc, double* out) {
+  __shared__ double red[kCT / 32];
+  const int64_t j = blockIdx.x;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += kCT) {
+    const double v = hypot(V[j * ld + i], V[j * ld + h + i]);
+    s += (v <= sc.eps) ? v * v / (sc.eps * sc.c2) : log((sc.p + v) / (sc.p + sc.eps)) / sc.c1 + sc.eps / sc.c2;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[j] = s;
+}
+__global__ void k_ce_build_target(const double* V, const double* T, const double* inv_xi, const double* rho, const double* absmin,
+                                  int q, StageConsts sc, int64_t m, int64_t h, int64_t ld, double* B) {
+  const int64_t j = blockIdx.y;
+  const double ixi = j < m ? inv_xi[j] : 0.0;
+  const bool sparse = j < q;
+  const double wmax = sparse ? weight_of_abs(absmin[j], sc) : 0.0;
+  const double rj = sparse ? rho[j] : 0.0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < h; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    double re, im;
+    if (i < m && j < m) {
+      double h1r = 0.0, h1i = 0.0;
+      if (sparse) {
+        const double vr = V[j * ld + i], vi = V[j * ld + h + i];
+        const double t = (weight_of_abs(hypot(vr, vi), sc) - wmax) * rj;        // R/spEigenCov.R:147-153
+        h1r = t * vr;
+        h1i = t * vi;
+      }
+      re = -(h1r + T[j * ld + i] * ixi);                                        // :154,:157
+      im = -(h1i + T[j * ld + h + i] * ixi);
+    } else {
+      re = (i == j) ? 1.0 : 0.0;
+      im = 0.0;
+    }
+    ce_store(B, ld, h, i, j, re, im);
+  }
+}
+__global__ void __launch_bounds__(kCT) k_ce_thres_norms(const double* V, int64_t m, int64_t h, int64_t ld, double thres, double* nrm2) {
+  __shared__ double red[kCT / 32];
+  const int64_t j = blockIdx.x;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += kCT) {
+    const double vr = V[j * ld + i], vi = V[j * ld + h + i];
+    if (!(hypot(vr, vi) < thres)) s += vr * vr + vi * vi;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) nrm2[j] = s;
+}
+__global__ void k_ce_thres_scale(const double* V, int64_t m, int64_t h, int64_t ld, double thres, const double* rs, const double* cs,
+                                 double* Out) {
+  const int64_t j = blockIdx.y;
+  const double cj = (cs && j < m) ? cs[j] : 1.0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < h; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    double re = 0.0, im = 0.0;
+    if (i < m && j < m) {
+      re = V[j * ld + i];
+      im = V[j * ld + h + i];
+      if (hypot(re, im) < thres) { re = 0.0; im = 0.0; }
+      const double f = (rs ? rs[i] : 1.0) * cj;
+      re *= f;
+      im *= f;
+    }
+    ce_store(Out, ld, h, i, j, re, im);
+  }
+}
+__global__ void k_ce_extract(const double* Src, int64_t m, int64_t h, int64_t ld, double* Dst) {
+  const int64_t j = blockIdx.y;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < m; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    Dst[2 * (j * m + i)] = Src[j * ld + i];
+    Dst[2 * (j * m + i) + 1] = Src[j * ld + h + i];
+  }
+}
+
 inline dim3 grid2(int64_t rows, int64_t cols) {
   int64_t bx = (rows + 255) / 256;
   if (bx > 64) bx = 64;
@@ -814,6 +927,59 @@ int launch_cm_colsums(const double* X, int64_t n, int64_t m, int64_t ld, double*
 }
 int launch_cm_center(double* X, int64_t n, int64_t m, int64_t ld, const double* sums, double inv_n, cudaStream_t st) {
   k_cm_center<<<grid2(n, m), 256, 0, st>>>(X, n, ld, sums, inv_n);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+
+int launch_ce_embed(const double* Src, int64_t m, double* Dst, int64_t h, int64_t ld, double shift, double pad_diag, cudaStream_t st) {
+  k_ce_embed<<<grid2(h, h), 256, 0, st>>>(Src, m, Dst, h, ld, shift, pad_diag);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_ce_select_eigvecs(const double* W, const int* perm, int64_t m, int64_t h, int64_t ld, double* V, cudaStream_t st) {
+  k_ce_select_eigvecs<<<grid2(h, h), 256, 0, st>>>(W, perm, m, h, ld, V);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_ce_colabsmin(const double* V, int64_t m, int64_t h, int64_t cols, int64_t ld, double* out, cudaStream_t st) {
+  if (cols <= 0) return SPEIGEN_OK;
+  k_ce_colabsmin<<<static_cast<unsigned>(cols), kCT, 0, st>>>(V, m, h, ld, out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_ce_penalty(const double* V, int64_t m, int64_t h, int64_t cols, int64_t ld, StageConsts sc, double* out, cudaStream_t st) {
+  if (cols <= 0) return SPEIGEN_OK;
+  k_ce_penalty<<<static_cast<unsigned>(cols), kCT, 0, st>>>(V, m, h, ld, sc, out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_ce_build_target(const double* V, const double* T, const double* inv_xi, const double* rho, const double* absmin,
+                           int q, StageConsts sc, int64_t m, int64_t h, int64_t ld, double* B, cudaStream_t st) {
+  k_ce_build_target<<<grid2(h, h), 256, 0, st>>>(V, T, inv_xi, rho, absmin, q, sc, m, h, ld, B);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_ce_thres_norms(const double* V, int64_t m, int64_t h, int64_t ld, double thres, double* nrm2, cudaStream_t st) {
+  k_ce_thres_norms<<<static_cast<unsigned>(m), kCT, 0, st>>>(V, m, h, ld, thres, nrm2);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_ce_thres_scale(const double* V, int64_t m, int64_t h, int64_t ld, double thres, const double* rs, const double* cs,
+                          double* Out, cudaStream_t st) {
+  k_ce_thres_scale<<<grid2(h, h), 256, 0, st>>>(V, m, h, ld, thres, rs, cs, Out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_ce_extract(const double* Src, int64_t m, int64_t h, int64_t ld, double* Dst, cudaStream_t st) {
+  k_ce_extract<<<grid2(m, m), 256, 0, st>>>(Src, m, h, ld, Dst);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

@@ -77,4 +77,30 @@ int launch_cm_colsums(const double* X, int64_t n, int64_t m, int64_t ld, double*
 // X[:, j] -= mean[j]
 int launch_cm_center(double* X, int64_t n, int64_t m, int64_t ld, const double* sums, double inv_n, cudaStream_t st);
 
+
+// ---- complex matrices in real embedded form ---------------------------------------------------------------------------
+// A complex m x m matrix C = Cr + i Ci is carried as the real 2h x 2h matrix [[Cr, -Ci], [Ci, Cr]] (h = m rounded up to 64;
+// rows/columns [0, h) hold real parts, [h, 2h) imaginary parts).  The embedding is a *-homomorphism: products, Hermitian
+// transposes, unitary / Hermitian-positive-definite factors and therefore polar factors map onto their real counterparts,
+// so the real GEMM and Jacobi kernels serve complex input unchanged.
+// Dst (2h x 2h, ld) <- embed(Src - shift*I), Src = m x m column-major interleaved {re, im}; padded diagonal = pad_diag
+int launch_ce_embed(const double* Src_interleaved, int64_t m, double* Dst, int64_t h, int64_t ld, double shift,
+                    double pad_diag, cudaStream_t st);
+// V (embedded) <- complex eigenvectors x + i y taken from the real eigenvectors [x; y] = W[:, perm[j]], j < m; unit vectors beyond
+int launch_ce_select_eigvecs(const double* W, const int* perm, int64_t m, int64_t h, int64_t ld, double* V, cudaStream_t st);
+// out[j] = min_i |V[i,j]| (complex modulus), j < cols
+int launch_ce_colabsmin(const double* V, int64_t m, int64_t h, int64_t cols, int64_t ld, double* out, cudaStream_t st);
+// out[j] = sum_i g(|V[i,j]|)
+int launch_ce_penalty(const double* V, int64_t m, int64_t h, int64_t cols, int64_t ld, StageConsts sc, double* out, cudaStream_t st);
+// embedded Procrustes target (R/spEigenCov.R:147-157 for complex V)
+int launch_ce_build_target(const double* V, const double* T, const double* inv_xi, const double* rho, const double* absmin,
+                           int q, StageConsts sc, int64_t m, int64_t h, int64_t ld, double* B, cudaStream_t st);
+// nrm2[j] = sum_i |v_ij|^2 over entries with |v_ij| >= thres
+int launch_ce_thres_norms(const double* V, int64_t m, int64_t h, int64_t ld, double thres, double* nrm2, cudaStream_t st);
+// Out (embedded) <- embed( (|v| < thres ? 0 : v) * rs[i] * cs[j] ), zero padding
+int launch_ce_thres_scale(const double* V, int64_t m, int64_t h, int64_t ld, double thres, const double* rs, const double* cs,
+                          double* Out, cudaStream_t st);
+// Dst (m x m interleaved complex, column-major) <- the complex matrix carried by the embedded Src
+int launch_ce_extract(const double* Src, int64_t m, int64_t h, int64_t ld, double* Dst_interleaved, cudaStream_t st);
+
 }  // namespace speigen

@@ -148,7 +148,7 @@ def _check_against_oracle(S, q, Vq=None, rho=0.5):
     assert np.all(colwise_inner(r["vectors"][:, :q], ro["vectors"][:, :q]) > 1 - 1e-8)
     assert rel(r["cov"], ro["cov"]) < 1e-6
     m = S.shape[0]
-    assert np.abs(r["vectors"].T @ r["vectors"] - np.eye(m)).max() < 1e-8     # thresholding perturbs at ~thres
+    assert np.abs(np.conj(r["vectors"].T) @ r["vectors"] - np.eye(m)).max() < 1e-8     # thresholding perturbs at ~thres
     if Vq is not None:
         assert np.all(colwise_inner(r["vectors"][:, :q], Vq) > 0.999)
     return r, ro
@@ -174,6 +174,16 @@ def test_speigencov_readme_example():
     r, _ = _check_against_oracle(S, 3, Vq)
     R = np.eye(500) + (Vq * (100.0 * np.arange(3, 0, -1) - 1.0)) @ Vq.T
     assert np.linalg.norm(r["cov"] - R) < 0.85 * np.linalg.norm(S - R)
+
+
+def test_speigencov_complex():
+    """Complex Hermitian S (vignettes/SparseEigenvectors-vignette.Rmd:224-226): the real kernels on the embedded form."""
+    for m, n, seed in [(10, 15, 0), (60, 150, 5), (130, 400, 9)]:
+        X, Vq = o.spiked_samples(m, n, 3, 0.1 if m >= 30 else 0.3, seed=seed, cplx=True)
+        S = o.sample_cov(X)
+        r, ro = _check_against_oracle(S, 3)
+        assert np.iscomplexobj(r["vectors"]) and np.iscomplexobj(r["cov"])
+        assert np.abs(r["cov"] - np.conj(r["cov"].T)).max() < 1e-10 * np.abs(r["cov"]).max()
 
 
 def test_speigencov_errors():
