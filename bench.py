@@ -155,6 +155,61 @@ def cpu_mm_update_time(S_host, q, steps, threads):
     return steps / (time.perf_counter() - t0)
 
 
+def bench_speigencov(args):
+    """Secondary workload (BASELINE.json configs[4]): spEigenCov, m = 2000, n = 6000, q = 5, real FP64.
+    A step = one MM iteration of R/spEigenCov.R:97-124 (Procrustes update through the m x m polar factor + eigvalAlgo +
+    objective).  Everything is measured through the drop-in C ABI call with HOST buffers (speigencov_run_f64), so `value`
+    already contains the H2D of S and the D2H of vectors/values/cov; the roofline object is for the m x m x m FP64
+    tensor-core GEMM (bound: FP64 tensor pipe, peak = DMMA rate measured by tools/microbench/fp64_pipes.cu on this pool)."""
+    import sparseeigen_b200 as sb
+    from oracle import speigen_oracle as o
+    m, n, q = args.cov_m, args.cov_n, args.cov_q
+    X, Vq = o.spiked_samples(m, n, q, 0.05, seed=42)        # synthetic generator only
+    S = sb.cov(X)                                           # cov(X) on the device (symmetric DMMA GEMM)
+    sb.spEigenCov(S[:256, :256].copy(), 2)                  # warm the context
+    sampler = ClockSampler(0)
+    sampler.start()
+    calls, its, t_loop, t_gemm, gemms = max(1, args.steps // 10), 0, 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        r = sb.spEigenCov(S, q)
+        its += r["info"]["iterations"]; t_loop += r["info"]["seconds_loop"]
+        t_gemm += r["info"]["seconds_gemm"]; gemms += r["info"]["gemms"]
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    mp = (m + 127) // 128 * 128
+    tf = gemms * 2.0 * mp ** 3 / t_gemm / 1e12
+    peak_tf = 37.0
+    line = {"metric": "spEigenCov MM iters/sec (m=%d, n=%d, q=%d)" % (m, n, q), "value": its / dt, "unit": "MM iters/s", "n_gpus": 1,
+            "steps": its, "warmup": 1, "ms_per_step": 1e3 * dt / its, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "spEigenCov covariance input m=%d (cov of n=%d samples), q=%d, real FP64, spiked model card=0.05 seed 42" % (m, n, q),
+                       "step": "one MM iteration = 1 GEMM (S_hat V) + m x m polar factor (block Jacobi, 3 sweeps + 3 GEMMs) + eigvalAlgo + objective",
+                       "l2": "m x m matrices (33.5 MB each) are L2-resident by design; the call re-uploads S and re-creates its context every time",
+                       "timed_region": "whole speigencov_run_f64 calls incl. eigen(S), H2D of S, D2H of vectors/values/cov"},
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+                         "kernel": "k_gemm<1,1> (FP64 DMMA)", "ms_per_launch": 1e3 * t_gemm / gemms,
+                         "algorithmic_flops_per_launch": 2.0 * mp ** 3, "launches_timed": gemms,
+                         "peak_source": "FP64 tensor pipe measured on this pool (profiles/r01_microbench_fp64_pipes.log: DMMA.8x8x4 37.0 TFLOP/s); "
+                                        "MEASURED_PEAKS.json holds no FP64 figure",
+                         "note": "the GEMM is 4 % of the step; the step is bound by the latency of the Jacobi rounds (profiles/README.md)"},
+            "e2e": {"value": its / dt, "unit": "MM iters/s", "h2d_bytes_per_step": int(8 * m * m * calls / its),
+                    "d2h_bytes_per_step": int((2 * 8 * m * m + 8 * m) * calls / its), "calls": calls, "seconds_per_call": dt / calls,
+                    "api": "speigencov_run_f64 (one-shot .Call entry) on a host S"},
+            "gpu_launches": None, "clocks": clocks,
+            "full_solve": {"seconds_per_call": dt / calls, "seconds_loop": t_loop / calls, "iterations": its // calls,
+                           "eig_sweeps": r["info"]["eig_sweeps"], "svd_sweeps": r["info"]["svd_sweeps"],
+                           "recovery": [float(v) for v in np.abs(np.sum(r["vectors"][:, :q] * Vq, axis=0))]}}
+    if not args.no_cpu:
+        from oracle import speigencov_oracle as oc
+        t0 = time.perf_counter()
+        ro = oc.spEigenCov(S, q, return_trace=True)
+        tc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": len(ro["trace"].F) / tc, "unit": "MM iters/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "one full spEigenCov run of the oracle port (NumPy/OpenBLAS eigh + %d gesdd), %.1f s" % (len(ro["trace"].F), tc)}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,7 +225,16 @@ def main():
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-store exchange or NCCL allgather")
+    ap.add_argument("--workload", default="speigen", choices=["speigen", "speigencov"],
+                    help="speigen: the BASELINE metric (default); speigencov: BASELINE configs[4] (secondary line)")
+    ap.add_argument("--cov-m", type=int, default=2000)
+    ap.add_argument("--cov-n", type=int, default=6000)
+    ap.add_argument("--cov-q", type=int, default=5)
     args = ap.parse_args()
+    if args.workload == "speigencov" and args.impl == "ours":
+        if int(os.environ.get("RANK", "0")) == 0:
+            bench_speigencov(args)
+        return
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))

@@ -250,7 +250,8 @@ struct DenseCtx {
     }
     const int max_panels = static_cast<int>(mp / kJP);
     const int chunks = static_cast<int>(mp / kJRows);
-    jw.nsplit = std::max(1, std::min(chunks, 8));
+    jw.nsplit = std::max(1, std::min(chunks, 16));
+    if (const char* e = std::getenv("SPEIGEN_JACOBI_NSPLIT")) jw.nsplit = std::max(1, std::min(std::min(chunks, 16), std::atoi(e)));
     jw.inner_sweeps = 1;   // one 64 x 64 Jacobi sweep per panel visit: same outer sweep count as running it to convergence (measured)
     if (const char* e = std::getenv("SPEIGEN_JACOBI_INNER")) jw.inner_sweeps = std::atoi(e);
     if (const char* e = std::getenv("SPEIGEN_JACOBI_EARLY")) early_tol = std::atof(e);
@@ -313,6 +314,7 @@ struct DenseCtx {
     SPE_TRY2(launch_cm_identity(W, mp, ld, st));
     const int nblocks = static_cast<int>(mp / kJB);
     int sweeps = 0;
+    bool converged = false;
     for (; sweeps < max_sweeps;) {
       SPE_CUDA(cudaMemsetAsync(jw.offmax, 0, sizeof(double), st));
       for (int r = 0; r < nblocks; ++r) SPE_TRY2(launch_jacobi_round(X, W, mp, ld, r & 1, jw, st));
@@ -323,9 +325,13 @@ struct DenseCtx {
       // `off` is measured BEFORE each panel is rotated.  The cyclic Jacobi iteration converges quadratically, so a sweep
       // that started below `early_tol` ends near off^2 << jtol: the confirming sweep is skipped (the Newton-Schulz polish
       // of the callers squares the remaining non-orthogonality once more).
-      if (!(off > jtol) || off <= early_tol) break;
+      if (!(off > jtol) || off <= early_tol) { converged = true; break; }
     }
     if (sweeps_out) *sweeps_out = sweeps;
+    if (!converged) {
+      set_error("block Jacobi did not reach the orthogonality tolerance in %d sweeps (increase jacobi_max_sweeps)", sweeps);
+      return SPEIGEN_ERR_UNSUPPORTED;
+    }
     return SPEIGEN_OK;
   }
   // U = polar(B): B in `X` (destroyed), result in `U`; W, tmp are scratch matrices

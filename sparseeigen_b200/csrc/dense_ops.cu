@@ -326,8 +326,12 @@ __global__ void __launch_bounds__(1024) k_jeig(const double* gram_part, int nspl
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double* part = gram_part + static_cast<size_t>(p) * nsplit * (kJP * kJP);
   for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) {
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = (k < nsplit) ? __ldcg(part + static_cast<size_t>(k) * (kJP * kJP) + idx) : 0.0;   // all loads in flight
     double s = 0.0;
-    for (int k = 0; k < nsplit; ++k) s += part[static_cast<size_t>(k) * (kJP * kJP) + idx];   // fixed order
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += v[k];                                                                            // fixed order
     const int c = idx / kJP, r = idx - c * kJP;
     G[r * kEigPitch + c] = s;
     W[r * kEigPitch + c] = (r == c) ? 1.0 : 0.0;
@@ -391,13 +395,17 @@ __global__ void __launch_bounds__(1024) k_jeig(const double* gram_part, int nspl
           pair_of(r, lane, pi, qi);
           const double gpp = G[pi * kEigPitch + pi], gqq = G[qi * kEigPitch + qi], gpq = G[pi * kEigPitch + qi];
           double c = 1.0, sn = 0.0;
-          if (fabs(gpq) > eps * sqrt(fabs(gpp) * fabs(gqq))) {
-            // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (gqq - gpp) / (2 gpq), written with one sqrt and one division
+          if (gpq * gpq > (eps * eps) * fabs(gpp * gqq)) {
+            // zeta = (gqq - gpp) / (2 gpq), t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) = b / u with a = gqq - gpp, b = 2 gpq,
+            // u = a + sign(a) sqrt(a^2 + b^2);  c = 1 / sqrt(1 + t^2) = |u| / sqrt(u^2 + b^2), s = c t = sign(u) b / sqrt(u^2 + b^2):
+            // two reciprocal square roots, no division, and c^2 + s^2 = 1 by construction
             const double a = gqq - gpp, b = 2.0 * gpq;
-            const double rr = sqrt(fma(a, a, b * b));
-            const double tt = b / (a + (a >= 0.0 ? rr : -rr));
-            c = rsqrt(fma(tt, tt, 1.0));
-            sn = c * tt;
+            const double h2 = fma(a, a, b * b);
+            const double rr = h2 * rsqrt(h2);
+            const double u = a + (a >= 0.0 ? rr : -rr);
+            const double ir = rsqrt(fma(u, u, b * b));
+            c = fabs(u) * ir;
+            sn = (u >= 0.0 ? b : -b) * ir;
             any = 1;
           }
           s_c[lane] = c;
