@@ -280,6 +280,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):   # NCCL prints to stdout: keep it to ONE JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend="nccl", device_id=dev)
     lo, hi = sb.shard_range(m, world, rank)
     S = synth_cov_rows(m, n, q, args.card, lo, hi, dev)
