@@ -176,6 +176,30 @@ def test_speigencov_readme_example():
     assert np.linalg.norm(r["cov"] - R) < 0.85 * np.linalg.norm(S - R)
 
 
+def test_speigencov_config5_m2000():
+    """BASELINE.json configs[4]: spEigenCov, m = 2000, n = 6000, q = 5 (the vignette shape scaled up)."""
+    X, Vq = o.spiked_samples(2000, 6000, 5, 0.05, seed=42)
+    S = sb.cov(X)
+    assert rel(S, o.sample_cov(X)) < 1e-12
+    r, ro = _check_against_oracle(S, 5, Vq)
+    assert np.array_equal((r["vectors"][:, :5] != 0).sum(0), [100] * 5)
+    assert r["info"]["gemms"] >= r["info"]["iterations"] and r["info"]["seconds_gemm"] > 0
+
+
+def test_speigencov_q_variants():
+    X, Vq = o.spiked_samples(200, 500, 8, 0.05, seed=11)
+    S = o.sample_cov(X)
+    _check_against_oracle(S, 8, rho=0.3)
+    _check_against_oracle(S, 2, rho=0.9)
+    # q = 1: the reference stops inside eigvalAlgo (undefined `tmp`, R/spEigenCov.R:312) whenever the first eigenvalue
+    # needs no pooling; the drop-in pools {q} alone and completes
+    with pytest.raises(oc.EigvalAlgoError):
+        oc.spEigenCov(S, 1)
+    r = sb.spEigenCov(S, 1)
+    assert colwise_inner(r["vectors"][:, :1], Vq[:, :1])[0] > 0.999
+    assert np.abs(r["vectors"].T @ r["vectors"] - np.eye(200)).max() < 1e-8
+
+
 def test_speigencov_complex():
     """Complex Hermitian S (vignettes/SparseEigenvectors-vignette.Rmd:224-226): the real kernels on the embedded form."""
     for m, n, seed in [(10, 15, 0), (60, 150, 5), (130, 400, 9)]:
