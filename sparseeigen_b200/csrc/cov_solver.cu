@@ -213,7 +213,7 @@ struct DenseCtx {
   int* perm = nullptr;
   double* scan_part = nullptr;
   double* h_pinned = nullptr;        // 4*mp + 64 doubles
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_join = nullptr;
   double gemm_ms = 0.0;
   int gemms = 0;
   int max_sweeps = 40;
@@ -257,7 +257,19 @@ struct DenseCtx {
     if (const char* e = std::getenv("SPEIGEN_JACOBI_EARLY")) early_tol = std::atof(e);
     if (const char* e = std::getenv("SPEIGEN_JACOBI_VERBOSE")) verbose = std::atoi(e);
     SPE_CUDA(cudaMalloc(&jw.gram_part, static_cast<size_t>(max_panels) * jw.nsplit * kJP * kJP * sizeof(double)));
-    SPE_CUDA(cudaMalloc(&jw.wp, static_cast<size_t>(max_panels) * kJP * kJP * sizeof(double)));
+    jw.wp_stride = static_cast<size_t>(max_panels) * kJP * kJP;
+    SPE_CUDA(cudaMalloc(&jw.wp, JacobiWork::kWpSlots * jw.wp_stride * sizeof(double)));
+    {
+      const char* e = std::getenv("SPEIGEN_JACOBI_SIDE");
+      if (!(e && e[0] == '0')) {
+        SPE_CUDA(cudaStreamCreateWithFlags(&jw.side, cudaStreamNonBlocking));
+        for (int i = 0; i < JacobiWork::kWpSlots; ++i) {
+          SPE_CUDA(cudaEventCreateWithFlags(&jw.ev_eig[i], cudaEventDisableTiming));
+          SPE_CUDA(cudaEventCreateWithFlags(&jw.ev_applied[i], cudaEventDisableTiming));
+        }
+        SPE_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      }
+    }
     SPE_CUDA(cudaMalloc(&jw.offmax, sizeof(double)));
     for (auto& v : vec) SPE_CUDA(cudaMalloc(&v, static_cast<size_t>(mp) * sizeof(double)));
     SPE_CUDA(cudaMalloc(&perm, static_cast<size_t>(mp) * sizeof(int)));
@@ -273,6 +285,12 @@ struct DenseCtx {
     for (double* p : mats) cudaFree(p);
     mats.clear();
     cudaFree(jw.gram_part); cudaFree(jw.wp); cudaFree(jw.offmax);
+    if (jw.side) {
+      cudaStreamSynchronize(jw.side);
+      for (int i = 0; i < JacobiWork::kWpSlots; ++i) { cudaEventDestroy(jw.ev_eig[i]); cudaEventDestroy(jw.ev_applied[i]); }
+      cudaEventDestroy(ev_join);
+      cudaStreamDestroy(jw.side);
+    }
     for (auto& v : vec) { cudaFree(v); v = nullptr; }
     cudaFree(perm); cudaFree(scan_part);
     if (h_pinned) cudaFreeHost(h_pinned);
@@ -312,12 +330,21 @@ struct DenseCtx {
   // Block one-sided Jacobi: on exit X = X_in * W has mutually orthogonal columns, W orthogonal.
   int jacobi(double* X, double* W, int* sweeps_out) {
     SPE_TRY2(launch_cm_identity(W, mp, ld, st));
+    if (jw.side) {   // the side stream rotates W: it starts after the identity fill and joins at the end of every sweep
+      SPE_CUDA(cudaEventRecord(ev_join, st));
+      SPE_CUDA(cudaStreamWaitEvent(jw.side, ev_join, 0));
+    }
     const int nblocks = static_cast<int>(mp / kJB);
     int sweeps = 0;
+    int round_index = 0;
     bool converged = false;
     for (; sweeps < max_sweeps;) {
       SPE_CUDA(cudaMemsetAsync(jw.offmax, 0, sizeof(double), st));
-      for (int r = 0; r < nblocks; ++r) SPE_TRY2(launch_jacobi_round(X, W, mp, ld, r & 1, jw, st));
+      for (int r = 0; r < nblocks; ++r) SPE_TRY2(launch_jacobi_round(X, W, mp, ld, r & 1, jw, st, round_index++));
+      if (jw.side) {
+        SPE_CUDA(cudaEventRecord(ev_join, jw.side));
+        SPE_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+      }
       ++sweeps;
       double off = 0.0;
       SPE_TRY2(d2h(&off, jw.offmax, 1));

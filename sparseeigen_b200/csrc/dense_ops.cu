@@ -819,7 +819,8 @@ int launch_gemm(int64_t M, int64_t N, int64_t K, const GemmOperand& A, const Gem
   return launch_gemm_t<false, false>(ta, tb, prm, grid, st);
 }
 
-int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity, const JacobiWork& jw, cudaStream_t st) {
+int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity, const JacobiWork& jw, cudaStream_t st,
+                        int round_index) {
   const int nblocks = static_cast<int>(mp / kJB);
   const int npanels = nblocks / 2 - (parity ? 1 : 0);
   if (npanels <= 0) return SPEIGEN_OK;
@@ -837,13 +838,33 @@ int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity
     SPE_CUDA(cudaFuncSetAttribute(k_japply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_apply));
     attr_set = true;
   }
+  const int max_inner = jw.inner_sweeps == 0 ? 60 : (jw.inner_sweeps < 0 ? 0 : jw.inner_sweeps);
+  const unsigned chunks = static_cast<unsigned>(mp / kJRows);
+  if (!jw.side) {
+    k_jgram<<<dim3(npanels, jw.nsplit), 256, smem_gram, st>>>(X, mp, ld, col0, jw.nsplit, jw.gram_part);
+    SPE_CUDA(cudaGetLastError());
+    k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, max_inner);
+    SPE_CUDA(cudaGetLastError());
+    k_japply<<<dim3(npanels, chunks, 2), 256, smem_apply, st>>>(X, W, ld, col0, jw.wp);
+    SPE_CUDA(cudaGetLastError());
+    note_launch(3);
+    return SPEIGEN_OK;
+  }
+  const int slot = round_index % JacobiWork::kWpSlots;
+  double* wps = jw.wp + static_cast<size_t>(slot) * jw.wp_stride;
+  SPE_CUDA(cudaStreamWaitEvent(st, jw.ev_applied[slot], 0));      // the side stream has consumed this slot's previous rotation
   k_jgram<<<dim3(npanels, jw.nsplit), 256, smem_gram, st>>>(X, mp, ld, col0, jw.nsplit, jw.gram_part);
   SPE_CUDA(cudaGetLastError());
-  k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, jw.inner_sweeps == 0 ? 60 : (jw.inner_sweeps < 0 ? 0 : jw.inner_sweeps));
+  k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, wps, jw.offmax, max_inner);
   SPE_CUDA(cudaGetLastError());
-  k_japply<<<dim3(npanels, static_cast<unsigned>(mp / kJRows), 2), 256, smem_apply, st>>>(X, W, ld, col0, jw.wp);
+  SPE_CUDA(cudaEventRecord(jw.ev_eig[slot], st));
+  k_japply<<<dim3(npanels, chunks, 1), 256, smem_apply, st>>>(X, X, ld, col0, wps);
   SPE_CUDA(cudaGetLastError());
-  note_launch(3);
+  SPE_CUDA(cudaStreamWaitEvent(jw.side, jw.ev_eig[slot], 0));
+  k_japply<<<dim3(npanels, chunks, 1), 256, smem_apply, jw.side>>>(W, W, ld, col0, wps);
+  SPE_CUDA(cudaGetLastError());
+  SPE_CUDA(cudaEventRecord(jw.ev_applied[slot], jw.side));
+  note_launch(4);
   return SPEIGEN_OK;
 }
 

@@ -38,10 +38,18 @@ struct JacobiWork {
   double* offmax = nullptr;         // device scalar: max relative off-diagonal seen since the last reset
   int nsplit = 1;
   int inner_sweeps = 0;             // cap on the 64 x 64 Jacobi sweeps per panel visit (0 = run to convergence)
+  // The rotation of the accumulated right factor W is off the critical path (the next round's Gram needs only X): with a
+  // side stream it runs concurrently with the next round's Gram / 64 x 64 Jacobi (which occupies 32 of 148 SMs).
+  cudaStream_t side = nullptr;
+  static constexpr int kWpSlots = 4;             // ring of rotation buffers so jeig(r+1..r+3) never overwrites an unconsumed W_p
+  size_t wp_stride = 0;                          // doubles per slot
+  cudaEvent_t ev_eig[kWpSlots] = {};
+  cudaEvent_t ev_applied[kWpSlots] = {};
 };
 // One round of the odd-even block ordering on X (mp x mp, ld) and the accumulated right factor W (same shape):
 // parity 0 pairs blocks (0,1),(2,3),..; parity 1 pairs (1,2),(3,4),...
-int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity, const JacobiWork& jw, cudaStream_t st);
+int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity, const JacobiWork& jw, cudaStream_t st,
+                        int round_index = 0);
 
 // ---- column-major helpers --------------------------------------------------------------------------------------------
 // out[j] = sum_i A[i,j] * B[i,j]   (one block per column, fixed order; B == A gives squared column norms)
