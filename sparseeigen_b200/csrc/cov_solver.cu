@@ -257,6 +257,14 @@ struct DenseCtx {
     if (const char* e = std::getenv("SPEIGEN_JACOBI_EARLY")) early_tol = std::atof(e);
     if (const char* e = std::getenv("SPEIGEN_JACOBI_VERBOSE")) verbose = std::atoi(e);
     SPE_CUDA(cudaMalloc(&jw.gram_part, static_cast<size_t>(max_panels) * jw.nsplit * kJP * kJP * sizeof(double)));
+    {
+      const char* e = std::getenv("SPEIGEN_JEIG_SPLIT");
+      if (!(e && e[0] == '0')) {
+        SPE_CUDA(cudaMalloc(&jw.rot, static_cast<size_t>(max_panels) * (kJP - 1) * (kJP / 2) * 2 * sizeof(double)));
+        SPE_CUDA(cudaMalloc(&jw.flags, static_cast<size_t>(max_panels) * sizeof(int)));
+        SPE_CUDA(cudaMemset(jw.flags, 0, static_cast<size_t>(max_panels) * sizeof(int)));
+      }
+    }
     jw.wp_stride = static_cast<size_t>(max_panels) * kJP * kJP;
     SPE_CUDA(cudaMalloc(&jw.wp, JacobiWork::kWpSlots * jw.wp_stride * sizeof(double)));
     {
@@ -284,7 +292,7 @@ struct DenseCtx {
     cudaSetDevice(device);
     for (double* p : mats) cudaFree(p);
     mats.clear();
-    cudaFree(jw.gram_part); cudaFree(jw.wp); cudaFree(jw.offmax);
+    cudaFree(jw.gram_part); cudaFree(jw.wp); cudaFree(jw.offmax); cudaFree(jw.rot); cudaFree(jw.flags);
     if (jw.side) {
       cudaStreamSynchronize(jw.side);
       for (int i = 0; i < JacobiWork::kWpSlots; ++i) { cudaEventDestroy(jw.ev_eig[i]); cudaEventDestroy(jw.ev_applied[i]); }

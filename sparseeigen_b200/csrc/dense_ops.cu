@@ -454,6 +454,190 @@ __global__ void __launch_bounds__(1024) k_jeig(const double* gram_part, int nspl
   }
 }
 
+// Split form of k_jeig: two CTAs per panel on two SMs.  CTA 2p ("solver") runs the Jacobi sweep on the Gram matrix only and
+// publishes every round's 32 rotations (c, s) through global memory; CTA 2p + 1 ("builder") accumulates W = J_1 J_2 ... from
+// that list, one round behind.  The solver's round then carries half the shared-memory traffic and instructions; the
+// builder never feeds back into the solver, so its lag costs nothing but a short tail.  Handshake: the solver raises
+// `flag` to the number of published rounds (fence + volatile store), `-(n + 1)` when it has finished after n rounds; the
+// builder resets the flag to 0 before it exits (launches are stream-ordered).
+__global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, int nsplit, double* wp, double* offmax, int max_inner,
+                                                     double* rot, int* flags) {
+  extern __shared__ __align__(16) double sm_dyn[];
+  double* G = sm_dyn;                          // [64][65]: the Gram matrix (solver) or W (builder)
+  __shared__ double s_red[32];
+  __shared__ unsigned char s_pp[(kJP - 1) * (kJP / 2)], s_qq[(kJP - 1) * (kJP / 2)];
+  __shared__ double s_c[kJP / 2], s_s[kJP / 2];
+  __shared__ int s_flag;
+  const int p = blockIdx.x >> 1;
+  const bool builder = (blockIdx.x & 1) != 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kRoundsPerSweep = kJP - 1;
+  constexpr int kPairs = kJP / 2;
+  double* my_rot = rot + static_cast<size_t>(p) * (kRoundsPerSweep * kPairs * 2);     // [round][pair]{c, s} of the current sweep
+  volatile int* flag = flags + p;
+  for (int idx = threadIdx.x; idx < kRoundsPerSweep * kPairs; idx += blockDim.x) {
+    const int r = idx / kPairs, w = idx - r * kPairs;
+    int a, b;
+    if (w == 0) { a = kJP - 1; b = r; }
+    else { a = (r + w) % (kJP - 1); b = (r - w + (kJP - 1)) % (kJP - 1); }
+    s_pp[idx] = static_cast<unsigned char>(min(a, b));
+    s_qq[idx] = static_cast<unsigned char>(max(a, b));
+  }
+  const int ti = threadIdx.x >> 5;
+  const int tj = threadIdx.x & 31;
+
+  if (builder) {
+    // ------------------------------------------ W builder ------------------------------------------
+    double* W = G;
+    for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) {
+      const int c = idx / kJP, r = idx - c * kJP;
+      W[r * kEigPitch + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    int done_rounds = 0;
+    for (;;) {
+      if (threadIdx.x == 0) {
+        int f;
+        while ((f = *flag) == done_rounds) __nanosleep(32);
+        s_flag = f;
+      }
+      __syncthreads();
+      const int f = s_flag;
+      const int avail = f < 0 ? (-f - 1) : f;         // rounds published so far
+      __threadfence();
+      while (done_rounds < avail) {
+        const int r = done_rounds % kRoundsPerSweep;
+        if (threadIdx.x < kPairs) {
+          s_c[threadIdx.x] = __ldcg(my_rot + (static_cast<size_t>(r) * kPairs + threadIdx.x) * 2);
+          s_s[threadIdx.x] = __ldcg(my_rot + (static_cast<size_t>(r) * kPairs + threadIdx.x) * 2 + 1);
+        }
+        __syncthreads();
+        const double cj = s_c[tj], sj = s_s[tj];
+        if (sj != 0.0) {
+          const int pj = s_pp[r * kPairs + tj], qj = s_qq[r * kPairs + tj];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int row = ti * 2 + h;
+            const double w1 = W[row * kEigPitch + pj], w2 = W[row * kEigPitch + qj];
+            W[row * kEigPitch + pj] = cj * w1 - sj * w2;
+            W[row * kEigPitch + qj] = sj * w1 + cj * w2;
+          }
+        }
+        __syncthreads();
+        ++done_rounds;
+        // the solver reuses the rotation list every sweep: tell it this round's slot is free (only needed for max_inner > 1)
+      }
+      if (f < 0) break;
+    }
+    double* out = wp + static_cast<size_t>(p) * (kJP * kJP);
+    for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) {
+      const int j = idx / kJP, k = idx - j * kJP;
+      out[idx] = W[k * kEigPitch + ((j + kJB) & (kJP - 1))];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = 0;                   // ready for the next launch
+    return;
+  }
+
+  // -------------------------------------------- Gram solver --------------------------------------------
+  const double* part = gram_part + static_cast<size_t>(p) * nsplit * (kJP * kJP);
+  for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) {
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = (k < nsplit) ? __ldcg(part + static_cast<size_t>(k) * (kJP * kJP) + idx) : 0.0;
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sum += v[k];
+    const int c = idx / kJP, r = idx - c * kJP;
+    G[r * kEigPitch + c] = sum;
+  }
+  __syncthreads();
+  double mx = 0.0;
+  for (int rr = 0; rr < 2; ++rr) {
+    const int i = warp * 2 + rr;
+    const double gii = G[i * kEigPitch + i];
+    for (int j = lane; j < kJP; j += 32) {
+      if (j == i) continue;
+      const double gij = fabs(G[i * kEigPitch + j]);
+      if (gij == 0.0) continue;
+      const double den = sqrt(fabs(gii) * fabs(G[j * kEigPitch + j]));
+      mx = fmax(mx, den > 0.0 ? gij / den : 1.0e300);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    double v = s_red[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) {
+      s_red[0] = v;
+      atomicMax(reinterpret_cast<unsigned long long*>(offmax), static_cast<unsigned long long>(__double_as_longlong(v)));
+    }
+  }
+  __syncthreads();
+  const double panel_off = s_red[0];
+  const double eps = 2.220446049250313e-16;
+  int published = 0;
+  if (panel_off > eps) {
+    // the rotation list holds one sweep: with more than one inner sweep the solver would overwrite rounds the builder has
+    // not consumed yet, so the split form runs exactly one sweep per visit (the measured optimum; k_jeig covers the rest)
+    const int sweeps = max_inner > 0 ? 1 : 0;
+    for (int sweep = 0; sweep < sweeps; ++sweep) {
+      for (int r = 0; r < kRoundsPerSweep; ++r) {
+        if (warp == 0) {
+          const int pi = s_pp[r * kPairs + lane], qi = s_qq[r * kPairs + lane];
+          const double gpp = G[pi * kEigPitch + pi], gqq = G[qi * kEigPitch + qi], gpq = G[pi * kEigPitch + qi];
+          double c = 1.0, sn = 0.0;
+          if (gpq * gpq > (eps * eps) * fabs(gpp * gqq)) {
+            const double a = gqq - gpp, b = 2.0 * gpq;
+            const double h2 = fma(a, a, b * b);
+            const double rr = h2 * rsqrt(h2);
+            const double u = a + (a >= 0.0 ? rr : -rr);
+            const double ir = rsqrt(fma(u, u, b * b));
+            c = fabs(u) * ir;
+            sn = (u >= 0.0 ? b : -b) * ir;
+          }
+          s_c[lane] = c;
+          s_s[lane] = sn;
+          __stcg(my_rot + (static_cast<size_t>(r) * kPairs + lane) * 2, c);
+          __stcg(my_rot + (static_cast<size_t>(r) * kPairs + lane) * 2 + 1, sn);
+          ++published;
+          if ((r & 7) == 7 || r == kRoundsPerSweep - 1) {   // publish in batches of 8 rounds: the fence is the expensive part
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) *flag = published;
+          }
+        }
+        __syncthreads();
+        {
+          const int pi = s_pp[r * kPairs + ti], qi = s_qq[r * kPairs + ti];
+          const int pj = s_pp[r * kPairs + tj], qj = s_qq[r * kPairs + tj];
+          const double ci = s_c[ti], si = s_s[ti], cj = s_c[tj], sj = s_s[tj];
+          if (si != 0.0 || sj != 0.0) {
+            const double g00 = G[pi * kEigPitch + pj], g01 = G[pi * kEigPitch + qj];
+            const double g10 = G[qi * kEigPitch + pj], g11 = G[qi * kEigPitch + qj];
+            const double r00 = ci * g00 - si * g10, r01 = ci * g01 - si * g11;
+            const double r10 = si * g00 + ci * g10, r11 = si * g01 + ci * g11;
+            double n00 = cj * r00 - sj * r01, n01 = sj * r00 + cj * r01;
+            double n10 = cj * r10 - sj * r11, n11 = sj * r10 + cj * r11;
+            if (ti == tj) { n01 = 0.0; n10 = 0.0; }
+            G[pi * kEigPitch + pj] = n00; G[pi * kEigPitch + qj] = n01;
+            G[qi * kEigPitch + pj] = n10; G[qi * kEigPitch + qj] = n11;
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    *flag = -(published + 1);
+  }
+}
+
 // Mat[:, panel p] <- Mat[:, panel p] * Wp   for Mat in {X, W} (blockIdx.z), row chunk blockIdx.y; in place
 __global__ void __launch_bounds__(256) k_japply(double* X, double* Wt, int64_t ld, int col0, const double* wp) {
   extern __shared__ __align__(16) double sm_dyn[];
@@ -839,11 +1023,19 @@ int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity
     attr_set = true;
   }
   const int max_inner = jw.inner_sweeps == 0 ? 60 : (jw.inner_sweeps < 0 ? 0 : jw.inner_sweeps);
+  const bool split = jw.rot != nullptr && max_inner == 1;
+  const size_t smem_eig1 = static_cast<size_t>(kJP) * kEigPitch * sizeof(double);
+  static bool attr2_dev[64] = {};
+  if (split && !attr2_dev[dev_ & 63]) {
+    SPE_CUDA(cudaFuncSetAttribute(k_jeig_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eig1));
+    attr2_dev[dev_ & 63] = true;
+  }
   const unsigned chunks = static_cast<unsigned>(mp / kJRows);
   if (!jw.side) {
     k_jgram<<<dim3(npanels, jw.nsplit), 256, smem_gram, st>>>(X, mp, ld, col0, jw.nsplit, jw.gram_part);
     SPE_CUDA(cudaGetLastError());
-    k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, max_inner);
+    if (split) k_jeig_split<<<2 * npanels, 1024, smem_eig1, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, max_inner, jw.rot, jw.flags);
+    else k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, max_inner);
     SPE_CUDA(cudaGetLastError());
     k_japply<<<dim3(npanels, chunks, 2), 256, smem_apply, st>>>(X, W, ld, col0, jw.wp);
     SPE_CUDA(cudaGetLastError());
@@ -855,7 +1047,8 @@ int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity
   SPE_CUDA(cudaStreamWaitEvent(st, jw.ev_applied[slot], 0));      // the side stream has consumed this slot's previous rotation
   k_jgram<<<dim3(npanels, jw.nsplit), 256, smem_gram, st>>>(X, mp, ld, col0, jw.nsplit, jw.gram_part);
   SPE_CUDA(cudaGetLastError());
-  k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, wps, jw.offmax, max_inner);
+  if (split) k_jeig_split<<<2 * npanels, 1024, smem_eig1, st>>>(jw.gram_part, jw.nsplit, wps, jw.offmax, max_inner, jw.rot, jw.flags);
+  else k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, wps, jw.offmax, max_inner);
   SPE_CUDA(cudaGetLastError());
   SPE_CUDA(cudaEventRecord(jw.ev_eig[slot], st));
   k_japply<<<dim3(npanels, chunks, 1), 256, smem_apply, st>>>(X, X, ld, col0, wps);

@@ -40,6 +40,9 @@ struct JacobiWork {
   int inner_sweeps = 0;             // cap on the 64 x 64 Jacobi sweeps per panel visit (0 = run to convergence)
   // The rotation of the accumulated right factor W is off the critical path (the next round's Gram needs only X): with a
   // side stream it runs concurrently with the next round's Gram / 64 x 64 Jacobi (which occupies 32 of 148 SMs).
+  // split 64 x 64 Jacobi (k_jeig_split): per-panel rotation list [63][32]{c, s} and handshake flags (zero-initialised)
+  double* rot = nullptr;
+  int* flags = nullptr;
   cudaStream_t side = nullptr;
   static constexpr int kWpSlots = 4;             // ring of rotation buffers so jeig(r+1..r+3) never overwrites an unconsumed W_p
   size_t wp_stride = 0;                          // doubles per slot
