@@ -263,6 +263,7 @@ struct DenseCtx {
         SPE_CUDA(cudaMalloc(&jw.rot, static_cast<size_t>(max_panels) * (kJP - 1) * (kJP / 2) * 2 * sizeof(double)));
         SPE_CUDA(cudaMalloc(&jw.flags, static_cast<size_t>(max_panels) * sizeof(int)));
         SPE_CUDA(cudaMemset(jw.flags, 0, static_cast<size_t>(max_panels) * sizeof(int)));
+        if (const char* pe = std::getenv("SPEIGEN_JEIG_PUBLISH")) jw.publish_every = std::max(1, std::atoi(pe));
       }
     }
     jw.wp_stride = static_cast<size_t>(max_panels) * kJP * kJP;

@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(1024) k_jeig(const double* gram_part, int nspl
 // `flag` to the number of published rounds (fence + volatile store), `-(n + 1)` when it has finished after n rounds; the
 // builder resets the flag to 0 before it exits (launches are stream-ordered).
 __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, int nsplit, double* wp, double* offmax, int max_inner,
-                                                     double* rot, int* flags) {
+                                                     double* rot, int* flags, int publish_every) {
   extern __shared__ __align__(16) double sm_dyn[];
   double* G = sm_dyn;                          // [64][65]: the Gram matrix (solver) or W (builder)
   __shared__ double s_red[32];
@@ -485,10 +485,22 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
   }
   const int ti = threadIdx.x >> 5;
   const int tj = threadIdx.x & 31;
+  constexpr int kBlocksUpper = kPairs * (kPairs + 1) / 2;     // 528 pair-blocks (bi <= bj)
+  __shared__ unsigned char s_bi[kBlocksUpper], s_bj[kBlocksUpper];
+  if (!builder && threadIdx.x < kPairs * kPairs) {
+    const int bi = threadIdx.x / kPairs, bj = threadIdx.x - bi * kPairs;
+    if (bi <= bj) {
+      const int idx = bi * kPairs - bi * (bi - 1) / 2 + (bj - bi);   // row-major index inside the upper triangle
+      s_bi[idx] = static_cast<unsigned char>(bi);
+      s_bj[idx] = static_cast<unsigned char>(bj);
+    }
+  }
 
   if (builder) {
     // ------------------------------------------ W builder ------------------------------------------
     double* W = G;
+    double* rc = sm_dyn + kJP * kEigPitch;                 // staged rotations of one sweep: c[63][32]
+    double* rs = rc + kRoundsPerSweep * kPairs;            //                                s[63][32]
     for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) {
       const int c = idx / kJP, r = idx - c * kJP;
       W[r * kEigPitch + c] = (r == c) ? 1.0 : 0.0;
@@ -505,30 +517,36 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
       const int f = s_flag;
       const int avail = f < 0 ? (-f - 1) : f;         // rounds published so far
       __threadfence();
-      while (done_rounds < avail) {
-        const int r = done_rounds % kRoundsPerSweep;
-        if (threadIdx.x < kPairs) {
-          s_c[threadIdx.x] = __ldcg(my_rot + (static_cast<size_t>(r) * kPairs + threadIdx.x) * 2);
-          s_s[threadIdx.x] = __ldcg(my_rot + (static_cast<size_t>(r) * kPairs + threadIdx.x) * 2 + 1);
+      if (avail > done_rounds) {
+        // stage every newly published round at once (one L2 round trip per batch, not per round)
+        const int n_new = avail - done_rounds;
+        for (int idx = threadIdx.x; idx < n_new * kPairs; idx += blockDim.x) {
+          const int r = done_rounds + idx / kPairs, w = idx % kPairs;
+          rc[r * kPairs + w] = __ldcg(my_rot + (static_cast<size_t>(r) * kPairs + w) * 2);
+          rs[r * kPairs + w] = __ldcg(my_rot + (static_cast<size_t>(r) * kPairs + w) * 2 + 1);
         }
         __syncthreads();
-        const double cj = s_c[tj], sj = s_s[tj];
-        if (sj != 0.0) {
-          const int pj = s_pp[r * kPairs + tj], qj = s_qq[r * kPairs + tj];
+        // W' = W J_r: thread (ti, tj) owns rows 2 ti, 2 ti + 1 and the column pair tj of the round; every row lives in one
+        // warp (ti = warp index), so consecutive rounds only need a warp-level barrier
+        for (int r = done_rounds; r < avail; ++r) {
+          const double cj = rc[r * kPairs + tj], sj = rs[r * kPairs + tj];
+          if (sj != 0.0) {
+            const int pj = s_pp[r * kPairs + tj], qj = s_qq[r * kPairs + tj];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int row = ti * 2 + h;
-            const double w1 = W[row * kEigPitch + pj], w2 = W[row * kEigPitch + qj];
-            W[row * kEigPitch + pj] = cj * w1 - sj * w2;
-            W[row * kEigPitch + qj] = sj * w1 + cj * w2;
+            for (int h = 0; h < 2; ++h) {
+              const int row = ti * 2 + h;
+              const double w1 = W[row * kEigPitch + pj], w2 = W[row * kEigPitch + qj];
+              W[row * kEigPitch + pj] = cj * w1 - sj * w2;
+              W[row * kEigPitch + qj] = sj * w1 + cj * w2;
+            }
           }
+          __syncwarp();
         }
-        __syncthreads();
-        ++done_rounds;
-        // the solver reuses the rotation list every sweep: tell it this round's slot is free (only needed for max_inner > 1)
+        done_rounds = avail;
       }
       if (f < 0) break;
     }
+    __syncthreads();                                   // every warp has applied its last round
     double* out = wp + static_cast<size_t>(p) * (kJP * kJP);
     for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) {
       const int j = idx / kJP, k = idx - j * kJP;
@@ -605,27 +623,39 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
           __stcg(my_rot + (static_cast<size_t>(r) * kPairs + lane) * 2, c);
           __stcg(my_rot + (static_cast<size_t>(r) * kPairs + lane) * 2 + 1, sn);
           ++published;
-          if ((r & 7) == 7 || r == kRoundsPerSweep - 1) {   // publish in batches of 8 rounds: the fence is the expensive part
+          if ((r & (publish_every - 1)) == publish_every - 1 || r == kRoundsPerSweep - 1) {   // publish in batches: the fence is the expensive part
             __threadfence();
             __syncwarp();
             if (lane == 0) *flag = published;
           }
         }
         __syncthreads();
-        {
-          const int pi = s_pp[r * kPairs + ti], qi = s_qq[r * kPairs + ti];
-          const int pj = s_pp[r * kPairs + tj], qj = s_qq[r * kPairs + tj];
-          const double ci = s_c[ti], si = s_s[ti], cj = s_c[tj], sj = s_s[tj];
+        // G' = J^T G J as independent 2 x 2 blocks.  Only the upper triangle is kept (entry {a, b} lives at [min][max]):
+        // the 528 blocks bi <= bj are spread over 17 warps, halving the shared-memory wavefronts of the round.
+        if (threadIdx.x < kBlocksUpper) {
+          const int bi = s_bi[threadIdx.x], bj = s_bj[threadIdx.x];
+          const double ci = s_c[bi], si = s_s[bi], cj = s_c[bj], sj = s_s[bj];
           if (si != 0.0 || sj != 0.0) {
-            const double g00 = G[pi * kEigPitch + pj], g01 = G[pi * kEigPitch + qj];
-            const double g10 = G[qi * kEigPitch + pj], g11 = G[qi * kEigPitch + qj];
-            const double r00 = ci * g00 - si * g10, r01 = ci * g01 - si * g11;
-            const double r10 = si * g00 + ci * g10, r11 = si * g01 + ci * g11;
-            double n00 = cj * r00 - sj * r01, n01 = sj * r00 + cj * r01;
-            double n10 = cj * r10 - sj * r11, n11 = sj * r10 + cj * r11;
-            if (ti == tj) { n01 = 0.0; n10 = 0.0; }
-            G[pi * kEigPitch + pj] = n00; G[pi * kEigPitch + qj] = n01;
-            G[qi * kEigPitch + pj] = n10; G[qi * kEigPitch + qj] = n11;
+            const int pi = s_pp[r * kPairs + bi], qi = s_qq[r * kPairs + bi];
+            const int pj = s_pp[r * kPairs + bj], qj = s_qq[r * kPairs + bj];
+            if (bi == bj) {
+              const double g00 = G[pi * kEigPitch + pi], g01 = G[pi * kEigPitch + qi], g11 = G[qi * kEigPitch + qi];
+              const double r00 = ci * g00 - si * g01, r01 = ci * g01 - si * g11;
+              const double r10 = si * g00 + ci * g01, r11 = si * g01 + ci * g11;
+              G[pi * kEigPitch + pi] = ci * r00 - si * r01;
+              G[qi * kEigPitch + qi] = si * r10 + ci * r11;
+              G[pi * kEigPitch + qi] = 0.0;                   // the annihilated pair
+            } else {
+              double* e00 = G + min(pi, pj) * kEigPitch + max(pi, pj);
+              double* e01 = G + min(pi, qj) * kEigPitch + max(pi, qj);
+              double* e10 = G + min(qi, pj) * kEigPitch + max(qi, pj);
+              double* e11 = G + min(qi, qj) * kEigPitch + max(qi, qj);
+              const double g00 = *e00, g01 = *e01, g10 = *e10, g11 = *e11;
+              const double r00 = ci * g00 - si * g10, r01 = ci * g01 - si * g11;
+              const double r10 = si * g00 + ci * g10, r11 = si * g01 + ci * g11;
+              *e00 = cj * r00 - sj * r01; *e01 = sj * r00 + cj * r01;
+              *e10 = cj * r10 - sj * r11; *e11 = sj * r10 + cj * r11;
+            }
           }
         }
         __syncthreads();
@@ -1024,7 +1054,7 @@ int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity
   }
   const int max_inner = jw.inner_sweeps == 0 ? 60 : (jw.inner_sweeps < 0 ? 0 : jw.inner_sweeps);
   const bool split = jw.rot != nullptr && max_inner == 1;
-  const size_t smem_eig1 = static_cast<size_t>(kJP) * kEigPitch * sizeof(double);
+  const size_t smem_eig1 = (static_cast<size_t>(kJP) * kEigPitch + 2 * (kJP - 1) * (kJP / 2)) * sizeof(double);
   static bool attr2_dev[64] = {};
   if (split && !attr2_dev[dev_ & 63]) {
     SPE_CUDA(cudaFuncSetAttribute(k_jeig_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eig1));
@@ -1034,7 +1064,7 @@ int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity
   if (!jw.side) {
     k_jgram<<<dim3(npanels, jw.nsplit), 256, smem_gram, st>>>(X, mp, ld, col0, jw.nsplit, jw.gram_part);
     SPE_CUDA(cudaGetLastError());
-    if (split) k_jeig_split<<<2 * npanels, 1024, smem_eig1, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, max_inner, jw.rot, jw.flags);
+    if (split) k_jeig_split<<<2 * npanels, 1024, smem_eig1, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, max_inner, jw.rot, jw.flags, jw.publish_every);
     else k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, max_inner);
     SPE_CUDA(cudaGetLastError());
     k_japply<<<dim3(npanels, chunks, 2), 256, smem_apply, st>>>(X, W, ld, col0, jw.wp);
@@ -1047,7 +1077,7 @@ int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity
   SPE_CUDA(cudaStreamWaitEvent(st, jw.ev_applied[slot], 0));      // the side stream has consumed this slot's previous rotation
   k_jgram<<<dim3(npanels, jw.nsplit), 256, smem_gram, st>>>(X, mp, ld, col0, jw.nsplit, jw.gram_part);
   SPE_CUDA(cudaGetLastError());
-  if (split) k_jeig_split<<<2 * npanels, 1024, smem_eig1, st>>>(jw.gram_part, jw.nsplit, wps, jw.offmax, max_inner, jw.rot, jw.flags);
+  if (split) k_jeig_split<<<2 * npanels, 1024, smem_eig1, st>>>(jw.gram_part, jw.nsplit, wps, jw.offmax, max_inner, jw.rot, jw.flags, jw.publish_every);
   else k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, wps, jw.offmax, max_inner);
   SPE_CUDA(cudaGetLastError());
   SPE_CUDA(cudaEventRecord(jw.ev_eig[slot], st));
