@@ -280,7 +280,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):   # NCCL prints to stdout: keep it to ONE JSON line
+        # NCCL prints its version banner to stdout at NCCL_DEBUG >= VERSION (here it comes from an nccl.conf, not the env):
+        # keep stdout to ONE JSON line.  An explicit environment value takes precedence over the conf file.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend="nccl", device_id=dev)
     lo, hi = sb.shard_range(m, world, rank)
