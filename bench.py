@@ -25,6 +25,14 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# Libraries print to stdout behind our back (NCCL's "NCCL version ..." banner comes from a printf inside libnccl): the
+# process-level stdout is pointed at stderr for the whole run and the ONE JSON line is written to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 METRIC = "spEigen MM iters/sec (m=50k cov, q=20)"
 UNIT = "MM iters/s"
@@ -207,7 +215,7 @@ def bench_speigencov(args):
         tc = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": len(ro["trace"].F) / tc, "unit": "MM iters/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "one full spEigenCov run of the oracle port (NumPy/OpenBLAS eigh + %d gesdd), %.1f s" % (len(ro["trace"].F), tc)}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -268,7 +276,7 @@ def main():
                                  "sample": f"{steps} MM updates on the full {m}x{m} S"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ---------------------------------------------------------------- our arm (B200) -----------------
@@ -280,10 +288,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner to stdout at NCCL_DEBUG >= VERSION (here it comes from an nccl.conf, not the env):
-        # keep stdout to ONE JSON line.  An explicit environment value takes precedence over the conf file.
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend="nccl", device_id=dev)
     lo, hi = sb.shard_range(m, world, rank)
     S = synth_cov_rows(m, n, q, args.card, lo, hi, dev)
@@ -394,7 +398,7 @@ def main():
             line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_steps} MM updates (oracle port, direct-S mode, NumPy/OpenBLAS) on the full {m}x{m} S"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
