@@ -211,6 +211,22 @@ def test_speigencov_complex():
         assert np.abs(r["cov"] - np.conj(r["cov"].T)).max() < 1e-10 * np.abs(r["cov"]).max()
 
 
+@pytest.mark.parametrize("name", ["real_m40", "real_m64_rho09", "cplx_m30"])
+def test_speigencov_golden(name):
+    """Committed fixtures (tests/golden/speigencov_cases.npz, tools/make_golden_cov.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "speigencov_cases.npz"))
+    q = int(g[f"{name}.q"])
+    r = sb.spEigenCov(g[f"{name}.S"], q, float(g[f"{name}.rho"]))
+    F, Fg = r["info"]["F"], g[f"{name}.F"]
+    assert len(F) == len(Fg) and np.max(np.abs(F - Fg) / np.abs(Fg)) < 1e-9
+    assert np.array_equal(r["info"]["stage_of_k"], g[f"{name}.stage"])
+    assert np.max(np.abs(r["values"] - g[f"{name}.values"])) < 1e-8 * g[f"{name}.values"].max()
+    assert np.array_equal(r["vectors"][:, :q] != 0, g[f"{name}.vectors_q"] != 0)
+    assert np.all(colwise_inner(r["vectors"][:, :q], g[f"{name}.vectors_q"]) > 1 - 1e-8)
+    assert rel(r["cov"], g[f"{name}.cov"]) < 1e-6
+
+
 def test_speigencov_errors():
     rng = np.random.default_rng(0)
     S = o.sample_cov(rng.standard_normal((15, 10)))

@@ -169,3 +169,33 @@ def test_struct_layouts():
     sz = (ctypes.c_int32 * 2)()
     assert sb.lib().speigencov_struct_sizes(ctypes.byref(sz, 0), ctypes.byref(sz, 4)) == 0
     assert tuple(sz) == (ctypes.sizeof(sb.CovCfg), ctypes.sizeof(sb.CovOut))
+
+
+# ---- committed golden fixtures (tools/make_golden_cov.py; regression pins of the oracle, not R outputs) -------------------
+GOLDEN_CASES = ["real_m40", "real_m64_rho09", "cplx_m30"]
+
+
+def _golden_cov():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "speigencov_cases.npz"))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_reproduces_the_golden_fixtures(name):
+    g = _golden_cov()
+    r = oc.spEigenCov(g[f"{name}.S"], int(g[f"{name}.q"]), float(g[f"{name}.rho"]), return_trace=True)
+    q = int(g[f"{name}.q"])
+    F = np.array(r["trace"].F)
+    assert len(F) == len(g[f"{name}.F"]) and np.allclose(F, g[f"{name}.F"], rtol=1e-9)
+    assert np.array_equal(np.array(r["trace"].stage), g[f"{name}.stage"])
+    assert np.allclose(r["values"], g[f"{name}.values"], rtol=1e-8)
+    assert np.array_equal(r["vectors"][:, :q] != 0, g[f"{name}.vectors_q"] != 0)
+    inner = np.abs(np.sum(np.conj(r["vectors"][:, :q]) * g[f"{name}.vectors_q"], axis=0))
+    assert np.all(inner > 1 - 1e-8)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_eigval_algo_golden(name):
+    g = _golden_cov()
+    out = sb.eigval_algo(g[f"{name}.eigval_g"], float(g[f"{name}.eigval_x"]), int(g[f"{name}.q"]))
+    assert np.array_equal(out, g[f"{name}.eigval_out"])
