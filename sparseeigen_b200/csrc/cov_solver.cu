@@ -279,7 +279,7 @@ struct DenseCtx {
         SPE_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
       }
     }
-    SPE_CUDA(cudaMalloc(&jw.offmax, sizeof(double)));
+    SPE_CUDA(cudaMalloc(&jw.offmax, 2 * sizeof(double)));
     for (auto& v : vec) SPE_CUDA(cudaMalloc(&v, static_cast<size_t>(mp) * sizeof(double)));
     SPE_CUDA(cudaMalloc(&perm, static_cast<size_t>(mp) * sizeof(int)));
     SPE_CUDA(cudaMalloc(&scan_part, static_cast<size_t>(mp) * 4 * sizeof(double)));
@@ -348,15 +348,20 @@ struct DenseCtx {
     int round_index = 0;
     bool converged = false;
     for (; sweeps < max_sweeps;) {
-      SPE_CUDA(cudaMemsetAsync(jw.offmax, 0, sizeof(double), st));
+      SPE_CUDA(cudaMemsetAsync(jw.offmax, 0, 2 * sizeof(double), st));
       for (int r = 0; r < nblocks; ++r) SPE_TRY2(launch_jacobi_round(X, W, mp, ld, r & 1, jw, st, round_index++));
       if (jw.side) {
         SPE_CUDA(cudaEventRecord(ev_join, jw.side));
         SPE_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
       }
       ++sweeps;
-      double off = 0.0;
-      SPE_TRY2(d2h(&off, jw.offmax, 1));
+      double off2[2] = {0.0, 0.0};
+      SPE_TRY2(d2h(off2, jw.offmax, 2));
+      const double off = off2[0];
+      if (off2[1] != 0.0) {
+        set_error("block Jacobi: the rotation hand-off between the solver and builder CTAs timed out");
+        return SPEIGEN_ERR_CUDA;
+      }
       if (verbose) std::fprintf(stderr, "[jacobi] sweep %d max relative off-diagonal %.3e\n", sweeps, off);
       // `off` is measured BEFORE each panel is rotated.  The cyclic Jacobi iteration converges quadratically, so a sweep
       // that started below `early_tol` ends near off^2 << jtol: the confirming sweep is skipped (the Newton-Schulz polish

@@ -510,7 +510,15 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
     for (;;) {
       if (threadIdx.x == 0) {
         int f;
-        while ((f = *flag) == done_rounds) __nanosleep(32);
+        long long spins = 0;
+        while ((f = *flag) == done_rounds) {
+          __nanosleep(64);
+          if (++spins > (1LL << 25)) {        // > 2 s without news from the solver CTA: give up instead of hanging the GPU
+            offmax[1] = 1.0;                  // reported by the host as an error after the sweep
+            f = -(done_rounds + 1);
+            break;
+          }
+        }
         s_flag = f;
       }
       __syncthreads();

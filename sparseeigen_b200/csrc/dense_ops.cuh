@@ -35,7 +35,7 @@ constexpr int kJRows = 128;         // rows per tile in the panel kernels
 struct JacobiWork {
   double* gram_part = nullptr;      // [max_panels][nsplit][kJP*kJP]
   double* wp = nullptr;             // [max_panels][kJP*kJP] rotation of each panel (column-major, block swap folded in)
-  double* offmax = nullptr;         // device scalar: max relative off-diagonal seen since the last reset
+  double* offmax = nullptr;         // device [2]: max relative off-diagonal seen since the last reset; hand-off timeout flag
   int nsplit = 1;
   int inner_sweeps = 0;             // cap on the 64 x 64 Jacobi sweeps per panel visit (0 = run to convergence)
   // The rotation of the accumulated right factor W is off the critical path (the next round's Gram needs only X): with a
