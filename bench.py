@@ -170,9 +170,9 @@ def bench_speigencov(args):
     already contains the H2D of S and the D2H of vectors/values/cov; the roofline object is for the m x m x m FP64
     tensor-core GEMM (bound: FP64 tensor pipe, peak = DMMA rate measured by tools/microbench/fp64_pipes.cu on this pool)."""
     import sparseeigen_b200 as sb
-    from oracle import speigen_oracle as o
+    from sparseeigen_b200 import synth
     m, n, q = args.cov_m, args.cov_n, args.cov_q
-    X, Vq = o.spiked_samples(m, n, q, 0.05, seed=42)        # synthetic generator only
+    X, Vq = synth.spiked_samples(m, n, q, 0.05, seed=42)
     S = sb.cov(X)                                           # cov(X) on the device (symmetric DMMA GEMM)
     sb.spEigenCov(S[:256, :256].copy(), 2)                  # warm the context
     sampler = ClockSampler(0)

@@ -13,7 +13,8 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sparseeigen_b200 as sb                      # noqa: E402
-from oracle import speigen_oracle as o             # noqa: E402  (generator + checker)
+from sparseeigen_b200 import synth                 # noqa: E402
+from oracle import speigen_oracle as o             # noqa: E402  (the CPU port scored beside the product: checker only)
 
 
 def scores(U, Vq, m):
@@ -29,7 +30,7 @@ def main():
     ap.add_argument("--n", type=int, default=200)
     a = ap.parse_args()
     m, n, q = a.m, a.n, 3
-    X, Vq = o.spiked_samples(m, n, q, 0.1, seed=42)
+    X, Vq = synth.spiked_samples(m, n, q, 0.1, seed=42)
     lines = []
     for rho in (0.1, 0.5, 0.9):
         r = sb.spEigen(X, q, rho, data=True)

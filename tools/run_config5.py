@@ -23,8 +23,8 @@ def main():
     ap.add_argument("--oracle", action="store_true")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    from oracle import speigen_oracle as o         # generator only (and the checker when --oracle)
-    X, Vq = o.spiked_samples(a.m, a.n, a.q, a.card, seed=42)
+    from sparseeigen_b200 import synth
+    X, Vq = synth.spiked_samples(a.m, a.n, a.q, a.card, seed=42)
     t0 = time.time()
     S = sb.cov(X)                                  # cov(X) on the device (symmetric DMMA GEMM)
     t_cov = time.time() - t0

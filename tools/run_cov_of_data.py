@@ -23,9 +23,9 @@ def main():
     ap.add_argument("--card", type=float, default=0.02)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    from oracle import speigen_oracle as o         # synthetic generator only
+    from sparseeigen_b200 import synth
     t0 = time.time()
-    X, Vq = o.spiked_samples(a.m, a.n, a.q, a.card, seed=42)
+    X, Vq = synth.spiked_samples(a.m, a.n, a.q, a.card, seed=42)
     X = np.asfortranarray(X)
     t_gen = time.time() - t0
     # pure GEMM rate of the symmetric product (resident random operands, CUDA events)

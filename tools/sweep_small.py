@@ -4,13 +4,14 @@ import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import sparseeigen_b200 as sb
-from oracle import speigen_oracle as o
+from sparseeigen_b200 import synth
+from oracle import speigen_oracle as o      # the CPU port timed beside the product (baseline leg only)
 published = {100: 0.0140, 200: 0.0258, 300: 0.0342, 400: 0.0472, 500: 0.0614, 600: 0.0864, 700: 0.1206, 800: 0.1514}
 rows = []
-sb.spEigen(o.spiked_samples(100, 20, 3, 0.1, seed=1)[0], 3, data=True)      # context warm-up
+sb.spEigen(synth.spiked_samples(100, 20, 3, 0.1, seed=1)[0], 3, data=True)      # context warm-up
 for m in range(100, 900, 100):
     n = -(-m // 5)
-    X, Vq = o.spiked_samples(m, n, 3, 0.1, seed=m)
+    X, Vq = synth.spiked_samples(m, n, 3, 0.1, seed=m)
     reps = 20
     t0 = time.perf_counter()
     for _ in range(reps):
