@@ -264,6 +264,10 @@ struct DenseCtx {
         SPE_CUDA(cudaMalloc(&jw.flags, static_cast<size_t>(max_panels) * sizeof(int)));
         SPE_CUDA(cudaMemset(jw.flags, 0, static_cast<size_t>(max_panels) * sizeof(int)));
         if (const char* pe = std::getenv("SPEIGEN_JEIG_PUBLISH")) jw.publish_every = std::max(1, std::atoi(pe));
+        if (const char* te = std::getenv("SPEIGEN_JEIG_THREADS")) {
+          const int t = std::atoi(te);
+          if (t == 576 || t == 640 || t == 768 || t == 1024) jw.split_threads = t;
+        }
       }
     }
     jw.wp_stride = static_cast<size_t>(max_panels) * kJP * kJP;

@@ -487,14 +487,17 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
   const int tj = threadIdx.x & 31;
   constexpr int kBlocksUpper = kPairs * (kPairs + 1) / 2;     // 528 pair-blocks (bi <= bj)
   __shared__ unsigned char s_bi[kBlocksUpper], s_bj[kBlocksUpper];
-  if (!builder && threadIdx.x < kPairs * kPairs) {
-    const int bi = threadIdx.x / kPairs, bj = threadIdx.x - bi * kPairs;
-    if (bi <= bj) {
-      const int idx = bi * kPairs - bi * (bi - 1) / 2 + (bj - bi);   // row-major index inside the upper triangle
-      s_bi[idx] = static_cast<unsigned char>(bi);
-      s_bj[idx] = static_cast<unsigned char>(bj);
+  if (!builder) {
+    for (int t = threadIdx.x; t < kPairs * kPairs; t += blockDim.x) {
+      const int bi = t / kPairs, bj = t - bi * kPairs;
+      if (bi <= bj) {
+        const int idx = bi * kPairs - bi * (bi - 1) / 2 + (bj - bi);   // row-major index inside the upper triangle
+        s_bi[idx] = static_cast<unsigned char>(bi);
+        s_bj[idx] = static_cast<unsigned char>(bj);
+      }
     }
   }
+  const int nwarps = blockDim.x >> 5;
 
   if (builder) {
     // ------------------------------------------ W builder ------------------------------------------
@@ -536,19 +539,21 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
         __syncthreads();
         // W' = W J_r: thread (ti, tj) owns rows 2 ti, 2 ti + 1 and the column pair tj of the round; every row lives in one
         // warp (ti = warp index), so consecutive rounds only need a warp-level barrier
-        for (int r = done_rounds; r < avail; ++r) {
-          const double cj = rc[r * kPairs + tj], sj = rs[r * kPairs + tj];
-          if (sj != 0.0) {
-            const int pj = s_pp[r * kPairs + tj], qj = s_qq[r * kPairs + tj];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int row = ti * 2 + h;
-              const double w1 = W[row * kEigPitch + pj], w2 = W[row * kEigPitch + qj];
-              W[row * kEigPitch + pj] = cj * w1 - sj * w2;
-              W[row * kEigPitch + qj] = sj * w1 + cj * w2;
+        const int rows_per_warp = nwarps >= 32 ? 2 : 4;            // 32 warps x 2 rows or 16 warps x 4 rows
+        if (ti * rows_per_warp < kJP) {
+          for (int r = done_rounds; r < avail; ++r) {
+            const double cj = rc[r * kPairs + tj], sj = rs[r * kPairs + tj];
+            if (sj != 0.0) {
+              const int pj = s_pp[r * kPairs + tj], qj = s_qq[r * kPairs + tj];
+              for (int h = 0; h < rows_per_warp; ++h) {
+                const int row = ti * rows_per_warp + h;
+                const double w1 = W[row * kEigPitch + pj], w2 = W[row * kEigPitch + qj];
+                W[row * kEigPitch + pj] = cj * w1 - sj * w2;
+                W[row * kEigPitch + qj] = sj * w1 + cj * w2;
+              }
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
         done_rounds = avail;
       }
@@ -579,8 +584,7 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
   }
   __syncthreads();
   double mx = 0.0;
-  for (int rr = 0; rr < 2; ++rr) {
-    const int i = warp * 2 + rr;
+  for (int i = warp; i < kJP; i += nwarps) {
     const double gii = G[i * kEigPitch + i];
     for (int j = lane; j < kJP; j += 32) {
       if (j == i) continue;
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
   if (lane == 0) s_red[warp] = mx;
   __syncthreads();
   if (warp == 0) {
-    double v = s_red[lane];
+    double v = lane < nwarps ? s_red[lane] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0) {
@@ -1072,7 +1076,7 @@ int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity
   if (!jw.side) {
     k_jgram<<<dim3(npanels, jw.nsplit), 256, smem_gram, st>>>(X, mp, ld, col0, jw.nsplit, jw.gram_part);
     SPE_CUDA(cudaGetLastError());
-    if (split) k_jeig_split<<<2 * npanels, 1024, smem_eig1, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, max_inner, jw.rot, jw.flags, jw.publish_every);
+    if (split) k_jeig_split<<<2 * npanels, jw.split_threads, smem_eig1, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, max_inner, jw.rot, jw.flags, jw.publish_every);
     else k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, jw.wp, jw.offmax, max_inner);
     SPE_CUDA(cudaGetLastError());
     k_japply<<<dim3(npanels, chunks, 2), 256, smem_apply, st>>>(X, W, ld, col0, jw.wp);
@@ -1085,7 +1089,7 @@ int launch_jacobi_round(double* X, double* W, int64_t mp, int64_t ld, int parity
   SPE_CUDA(cudaStreamWaitEvent(st, jw.ev_applied[slot], 0));      // the side stream has consumed this slot's previous rotation
   k_jgram<<<dim3(npanels, jw.nsplit), 256, smem_gram, st>>>(X, mp, ld, col0, jw.nsplit, jw.gram_part);
   SPE_CUDA(cudaGetLastError());
-  if (split) k_jeig_split<<<2 * npanels, 1024, smem_eig1, st>>>(jw.gram_part, jw.nsplit, wps, jw.offmax, max_inner, jw.rot, jw.flags, jw.publish_every);
+  if (split) k_jeig_split<<<2 * npanels, jw.split_threads, smem_eig1, st>>>(jw.gram_part, jw.nsplit, wps, jw.offmax, max_inner, jw.rot, jw.flags, jw.publish_every);
   else k_jeig<<<npanels, 1024, smem_eig, st>>>(jw.gram_part, jw.nsplit, wps, jw.offmax, max_inner);
   SPE_CUDA(cudaGetLastError());
   SPE_CUDA(cudaEventRecord(jw.ev_eig[slot], st));

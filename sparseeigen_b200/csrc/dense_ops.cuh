@@ -43,6 +43,7 @@ struct JacobiWork {
   // split 64 x 64 Jacobi (k_jeig_split): per-panel rotation list [63][32]{c, s} and handshake flags (zero-initialised)
   double* rot = nullptr;
   int* flags = nullptr;
+  int split_threads = 1024;        // CTA size of k_jeig_split (>= 544: the solver updates 528 blocks; 16 or 32 builder warps)
   int publish_every = 8;           // rounds per publish of the rotation list (power of two; 64 = once per sweep)
   cudaStream_t side = nullptr;
   static constexpr int kWpSlots = 4;             // ring of rotation buffers so jeig(r+1..r+3) never overwrites an unconsumed W_p
