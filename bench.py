@@ -178,12 +178,14 @@ def bench_speigencov(args):
     sampler = ClockSampler(0)
     sampler.start()
     calls, its, t_loop, t_gemm, gemms = max(1, args.steps // 10), 0, 0.0, 0.0, 0
+    l0 = int(sb.lib().speigen_solver_launch_count(None))      # process-wide count of the library's kernel launches
     t0 = time.perf_counter()
     for _ in range(calls):
         r = sb.spEigenCov(S, q)
         its += r["info"]["iterations"]; t_loop += r["info"]["seconds_loop"]
         t_gemm += r["info"]["seconds_gemm"]; gemms += r["info"]["gemms"]
     dt = time.perf_counter() - t0
+    launches = int(sb.lib().speigen_solver_launch_count(None)) - l0
     clocks = sampler.stop()
     mp = (m + 127) // 128 * 128
     tf = gemms * 2.0 * mp ** 3 / t_gemm / 1e12
@@ -204,7 +206,7 @@ def bench_speigencov(args):
             "e2e": {"value": its / dt, "unit": "MM iters/s", "h2d_bytes_per_step": int(8 * m * m * calls / its),
                     "d2h_bytes_per_step": int((2 * 8 * m * m + 8 * m) * calls / its), "calls": calls, "seconds_per_call": dt / calls,
                     "api": "speigencov_run_f64 (one-shot .Call entry) on a host S"},
-            "gpu_launches": None, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks,
             "full_solve": {"seconds_per_call": dt / calls, "seconds_loop": t_loop / calls, "iterations": its // calls,
                            "eig_sweeps": r["info"]["eig_sweeps"], "svd_sweeps": r["info"]["svd_sweeps"],
                            "recovery": [float(v) for v in np.abs(np.sum(r["vectors"][:, :q] * Vq, axis=0))]}}

@@ -44,6 +44,17 @@ def _worker(rank, world, port, ret):
         for r in range(world):                             # rank order => identical bits on every rank
             G = G + parts[r].numpy()
         ok_data = np.allclose(G, X.T @ (X @ U), rtol=1e-12, atol=1e-12)
+        # --- cov(X) formed shard by shard (speigen_solver_load_cov_of_data): rank r computes the column slab
+        #     S[:, lo:hi] = Xc^T Xc[:, lo:hi] / (n - 1) of its rows; together the slabs are cov(X) ------------------------
+        lo, hi = sb.shard_range(m, world, rank)
+        Xc = X - X.mean(axis=0, keepdims=True)
+        slab = np.zeros((m, per))
+        slab[:, :hi - lo] = Xc.T @ Xc[:, lo:hi] / (n - 1)
+        slabs = [torch.zeros(m, per, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(slabs, torch.from_numpy(slab))
+        Sfull = torch.cat(slabs, dim=1)[:, :m].numpy()
+        ok_covx = np.allclose(Sfull, np.cov(X, rowvar=False), rtol=1e-13, atol=1e-13)
+        ok_cov = ok_cov and ok_covx
         bits = torch.from_numpy(G.copy())
         ref = bits.clone()
         dist.broadcast(ref, src=0)
