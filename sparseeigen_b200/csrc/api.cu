@@ -10,6 +10,7 @@
 namespace speigen {
 const char* last_error();
 long long launch_count();
+void release_cov_context();   // cov_solver.cu: the dense context speigencov_run_* keeps between calls
 }  // namespace speigen
 using namespace speigen;
 
@@ -348,6 +349,7 @@ static speigen_cfg g_cached_cfg;
 int speigen_shutdown(void) {
   DeviceRestore restore_device__;
   if (g_cached) { speigen_solver_destroy(g_cached); g_cached = nullptr; }
+  release_cov_context();
   return SPEIGEN_OK;
 }
 

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <vector>
 
@@ -488,17 +489,41 @@ struct DenseCtx {
 // ---------------------------------------------------------------------------------------------------------------
 // spEigenCov driver
 // ---------------------------------------------------------------------------------------------------------------
+static DenseCtx* g_cov_ctx = nullptr;
+static std::mutex g_cov_mtx;
+static void release_cov_context_locked() {
+  if (g_cov_ctx) {
+    g_cov_ctx->destroy();
+    delete g_cov_ctx;
+    g_cov_ctx = nullptr;
+  }
+}
+
 // cplx: S_host is interleaved {re, im}; every m x m matrix is carried in real embedded form of dimension 2h (dense_ops.cuh)
 static int run_speigencov(const double* S_host, int64_t m, int q, double rho, double thres, const speigencov_cfg& cfg,
                           speigencov_out* out, bool cplx) {
-  DenseCtx cx;
   const double t_start = now_s();
   const int64_t h = cplx ? round_up(m, 64) : 0;
-  // matrices: 0 S_hat, 1 V, 2 T, 3 X (Jacobi work / target), 4 W, 5 tmp, 6 raw S (m x m in an mp x ld buffer; complex: flat)
-  int rc = cx.create(cfg.device, cplx ? 2 * h : m, 7);
-  if (rc != SPEIGEN_OK) { cx.destroy(); return rc; }
+  const int64_t dim = cplx ? 2 * h : m;
+  // One context (7 matrices of the padded dimension, Jacobi work space, streams) is kept alive between calls of the same
+  // size on the same device: creating and freeing it costs ~40 ms of a 0.5 s call at m = 2000.  speigen_shutdown() or
+  // process exit releases it; contexts above 4 GB are not kept.
+  std::lock_guard<std::mutex> lock(g_cov_mtx);
+  if (g_cov_ctx && (g_cov_ctx->device != cfg.device || g_cov_ctx->m != dim)) release_cov_context_locked();
+  int rc = SPEIGEN_OK;
+  if (!g_cov_ctx) {
+    g_cov_ctx = new DenseCtx();
+    // matrices: 0 S_hat, 1 V, 2 T, 3 X (Jacobi work / target), 4 W, 5 tmp, 6 raw S (m x m in an mp x ld buffer; complex: flat)
+    rc = g_cov_ctx->create(cfg.device, dim, 7);
+    if (rc != SPEIGEN_OK) { release_cov_context_locked(); return rc; }
+  } else {
+    SPE_CUDA(cudaSetDevice(cfg.device));
+  }
+  DenseCtx& cx = *g_cov_ctx;
+  cx.gemm_ms = 0.0;
+  cx.gemms = 0;
   cx.max_sweeps = cfg.jacobi_max_sweeps > 0 ? cfg.jacobi_max_sweeps : 40;
-  if (cfg.jacobi_tol > 0.0) cx.jtol = cfg.jacobi_tol;
+  cx.jtol = cfg.jacobi_tol > 0.0 ? cfg.jacobi_tol : std::sqrt(static_cast<double>(cx.mp)) * 2.220446049250313e-16;
   auto body = [&]() -> int {
     const int64_t mp = cx.mp, ld = cx.ld;
     double *Sh = cx.mats[0], *V = cx.mats[1], *T = cx.mats[2], *X = cx.mats[3], *W = cx.mats[4], *tmp = cx.mats[5],
@@ -667,8 +692,14 @@ static int run_speigencov(const double* S_host, int64_t m, int q, double rho, do
     return SPEIGEN_OK;
   };
   rc = body();
-  cx.destroy();
+  const size_t ctx_bytes = static_cast<size_t>(7) * cx.mp * cx.ld * sizeof(double);
+  if (rc != SPEIGEN_OK || ctx_bytes > (static_cast<size_t>(4) << 30)) release_cov_context_locked();
   return rc;
+}
+
+void release_cov_context() {
+  std::lock_guard<std::mutex> lock(g_cov_mtx);
+  release_cov_context_locked();
 }
 
 }  // namespace speigen
