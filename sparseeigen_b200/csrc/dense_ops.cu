@@ -466,7 +466,6 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
   double* G = sm_dyn;                          // [64][65]: the Gram matrix (solver) or W (builder)
   __shared__ double s_red[32];
   __shared__ unsigned char s_pp[(kJP - 1) * (kJP / 2)], s_qq[(kJP - 1) * (kJP / 2)];
-  __shared__ double s_c[kJP / 2], s_s[kJP / 2];
   __shared__ int s_flag;
   const int p = blockIdx.x >> 1;
   const bool builder = (blockIdx.x & 1) != 0;
@@ -610,7 +609,9 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
   __syncthreads();
   const double panel_off = s_red[0];
   const double eps = 2.220446049250313e-16;
-  int published = 0;
+  int published = 0, first_unpublished = 0;
+  double* src = sm_dyn + kJP * kEigPitch;                  // rotations of the sweep: c[63][32]
+  double* srs = src + kRoundsPerSweep * kPairs;            //                         s[63][32]
   if (panel_off > eps) {
     // the rotation list holds one sweep: with more than one inner sweep the solver would overwrite rounds the builder has
     // not consumed yet, so the split form runs exactly one sweep per visit (the measured optimum; k_jeig covers the rest)
@@ -630,12 +631,18 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
             c = fabs(u) * ir;
             sn = (u >= 0.0 ? b : -b) * ir;
           }
-          s_c[lane] = c;
-          s_s[lane] = sn;
-          __stcg(my_rot + (static_cast<size_t>(r) * kPairs + lane) * 2, c);
-          __stcg(my_rot + (static_cast<size_t>(r) * kPairs + lane) * 2 + 1, sn);
+          src[r * kPairs + lane] = c;
+          srs[r * kPairs + lane] = sn;
           ++published;
-          if ((r & (publish_every - 1)) == publish_every - 1 || r == kRoundsPerSweep - 1) {   // publish in batches: the fence is the expensive part
+          // The rotations go to global memory in batches: a CTA barrier waits for the strong global stores issued before it
+          // to be performed at L2, so storing every round would put an L2 round trip on the critical path of every round.
+          if ((r & (publish_every - 1)) == publish_every - 1 || r == kRoundsPerSweep - 1) {
+            __syncwarp();
+            for (int idx = first_unpublished * kPairs + lane; idx < published * kPairs; idx += 32) {
+              __stcg(my_rot + static_cast<size_t>(idx) * 2, src[idx]);
+              __stcg(my_rot + static_cast<size_t>(idx) * 2 + 1, srs[idx]);
+            }
+            first_unpublished = published;
             __threadfence();
             __syncwarp();
             if (lane == 0) *flag = published;
@@ -646,7 +653,7 @@ __global__ void __launch_bounds__(1024) k_jeig_split(const double* gram_part, in
         // the 528 blocks bi <= bj are spread over 17 warps, halving the shared-memory wavefronts of the round.
         if (threadIdx.x < kBlocksUpper) {
           const int bi = s_bi[threadIdx.x], bj = s_bj[threadIdx.x];
-          const double ci = s_c[bi], si = s_s[bi], cj = s_c[bj], sj = s_s[bj];
+          const double ci = src[r * kPairs + bi], si = srs[r * kPairs + bi], cj = src[r * kPairs + bj], sj = srs[r * kPairs + bj];
           if (si != 0.0 || sj != 0.0) {
             const int pi = s_pp[r * kPairs + bi], qi = s_qq[r * kPairs + bi];
             const int pj = s_pp[r * kPairs + bj], qj = s_qq[r * kPairs + bj];
