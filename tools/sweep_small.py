@@ -13,17 +13,20 @@ for m in range(100, 900, 100):
     n = -(-m // 5)
     X, Vq = synth.spiked_samples(m, n, 3, 0.1, seed=m)
     reps = 20
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    ts = []
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
         r = sb.spEigen(X, 3, rho=0.5, data=True)
-    gpu = (time.perf_counter() - t0) / reps
+        ts.append(time.perf_counter() - t0)
+    first_call, ts = ts[0], ts[1:]          # the first call of a new shape re-creates the cached device context
+    gpu = float(np.mean(ts))
     t0 = time.perf_counter()
     for _ in range(3):
         ro = o.spEigen(X, 3, rho=0.5, data=True)
     cpu = (time.perf_counter() - t0) / 3
     rec = np.abs(np.sum(r["vectors"] * Vq, axis=0)).min()
     same = bool(np.array_equal(r["vectors"] != 0, ro["vectors"] != 0))
-    rows.append(dict(m=m, n=n, gpu_call_s=gpu, oracle_cpu_s=cpu, published_reference_s=published[m], iterations=r["info"]["iterations"],
+    rows.append(dict(m=m, n=n, gpu_call_s=gpu, gpu_call_median_s=float(np.median(ts)), gpu_call_max_s=float(np.max(ts)), first_call_s=first_call, oracle_cpu_s=cpu, published_reference_s=published[m], iterations=r["info"]["iterations"],
                      loop_s=r["info"]["seconds_loop"], init_s=r["info"]["seconds_init"], upload_s=r["info"]["seconds_upload"],
                      min_recovery=float(rec), support_equal_oracle=same))
     print(json.dumps(rows[-1]), flush=True)
