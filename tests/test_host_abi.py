@@ -184,3 +184,13 @@ def test_synthetic_generator_matches_the_oracles():
         a = synth.spiked_samples(50, 20, 3, 0.1, seed=7, cplx=cplx)
         b = o.spiked_samples(50, 20, 3, 0.1, seed=7, cplx=cplx)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_tools_and_entry_points_parse():
+    """Every script under tools/, bench.py and __graft_entry__.py is syntactically valid (they only run on the GPU box)."""
+    import ast
+    import glob
+    files = glob.glob(os.path.join(ROOT, "tools", "*.py")) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    assert len(files) >= 10
+    for f in files:
+        ast.parse(open(f).read(), filename=f)
