@@ -11,8 +11,8 @@ known-answers (README.md:103-121: recovery >= 0.999 and a covariance error about
 algebraic identities of the update (monotone objective within a stage, ordered eigenvalues, unitary iterate).
 
 Quirks of the reference kept on purpose (each is what R actually computes):
-  * `A` is formed once per iteration from the OLD `V`/`Xi` (:100) and reused for the eigenvalue update (:106) after
-    `V` has been replaced (:103);
+  * `A` is formed once per iteration from the OLD `V`/`Xi` (:104) and reused for the eigenvalue update (:110) after
+    `V` has been replaced (:107);
   * `seq(i:q)` (:215,:218) is `1..(q-i+1)`, not `i..q`;
   * the final normalisation `matrix(rep(nrm, m), ncol = m) * V` (:133) scales ROW i by `nrm[i]`;
   * q == 1 (:289-335): when no trailing value violates the order the inner loop reads an undefined `tmp` and R stops
@@ -29,9 +29,9 @@ from .speigen_oracle import SpEigenError, h, is_symmetric, stage_constants
 MAX_ITER = 3000          # R/spEigenCov.R:49
 K_STAGES = 5             # :80
 P1, PK = 1.0, 5.0        # :81-82
-PSD_TOL = -1e-10         # :63  (`<=`)
-RANK_TOL = 1e-9          # :65
-SHIFT = 1e-6             # :69
+PSD_TOL = -1e-10         # :64  (`<=`)
+RANK_TOL = 1e-9          # :66
+SHIFT = 1e-6             # :70
 MAX_PASSES = 10000       # cap on eigvalAlgo's `while (1)` (:171,:290), which has no exit on some inputs
 
 
@@ -226,7 +226,7 @@ def eigvec_update(V, A, S_hat, rho_vec, q, w0, c1, p, epsi):
 
 
 def penalty(Vq, c1, c2, p, epsi):
-    """g of R/spEigenCov.R:110-112."""
+    """g of R/spEigenCov.R:114-116."""
     a = np.abs(Vq)
     g = np.empty(a.shape)
     small = a <= epsi
@@ -249,7 +249,7 @@ def spEigenCov(S, q=1, rho=0.5, thres=1e-9, return_trace=False, keep_iterates=Fa
     cplx = np.iscomplexobj(S)
     S = S.astype(np.complex128 if cplx else np.float64)
     m = S.shape[1]
-    vals, vecs = np.linalg.eigh(S, UPLO="L")                  # eigen(S), :62
+    vals, vecs = np.linalg.eigh(S, UPLO="L")                  # eigen(S), :63
     vals, vecs = vals[::-1].copy(), vecs[:, ::-1].copy()
     if np.any(vals <= PSD_TOL):
         raise SpEigenError("The covariance matrix is not PSD.")
@@ -259,7 +259,7 @@ def spEigenCov(S, q=1, rho=0.5, thres=1e-9, return_trace=False, keep_iterates=Fa
     V = vecs
     Xi = vals
     Xi_max = Xi[0]
-    S_hat = S - (Xi_max + SHIFT) * np.eye(m)                  # :69
+    S_hat = S - (Xi_max + SHIFT) * np.eye(m)                  # :70
     rho_vec = rho * 10.0 * np.sqrt(np.sum(np.abs(S) ** 2)) * Xi[:q] / Xi[0]     # :73
     pp, Eps, tol = schedule()
     F_v = []
@@ -271,20 +271,20 @@ def spEigenCov(S, q=1, rho=0.5, thres=1e-9, return_trace=False, keep_iterates=Fa
         flg = 1
         while True:
             k += 1
-            A = V / Xi[None, :]                               # V %*% diag(1/Xi), :100
-            V = eigvec_update(V, A, S_hat, rho_vec, q, w0, c1, p, epsi)   # :103
-            G = -np.real(np.sum(np.conj(A) * (S_hat @ A), axis=0))       # Re(diag(-h(A) S_hat A)), :106-107
-            Xi = eigval_algo(G, Xi_max, q)                    # :107
-            g = penalty(V[:, :q], c1, c2, p, epsi)            # :110-112
+            A = V / Xi[None, :]                               # V %*% diag(1/Xi), :104
+            V = eigvec_update(V, A, S_hat, rho_vec, q, w0, c1, p, epsi)   # :107
+            G = -np.real(np.sum(np.conj(A) * (S_hat @ A), axis=0))       # Re(diag(-h(A) S_hat A)), :110-111
+            Xi = eigval_algo(G, Xi_max, q)                    # :111
+            g = penalty(V[:, :q], c1, c2, p, epsi)            # :114-116
             quad = np.real(np.sum(np.conj(V) * (S @ V), axis=0))
-            Fk = float(np.sum(np.log(Xi)) + np.sum(quad / Xi) + rho_vec @ g.sum(axis=0))   # :114
+            Fk = float(np.sum(np.log(Xi)) + np.sum(quad / Xi) + rho_vec @ g.sum(axis=0))   # :118
             F_v.append(Fk)
             tr.stage.append(ee + 1)
             tr.F.append(Fk)
             if keep_iterates:
                 tr.Xi.append(Xi.copy())
                 tr.V.append(V.copy())
-            if flg == 0:                                      # :117-122
+            if flg == 0:                                      # :121-126
                 rel_change = abs(F_v[k - 1] - F_v[k - 2]) / max(1.0, abs(F_v[k - 2]))
                 if rel_change <= tol[ee] or k >= max_iter:
                     break

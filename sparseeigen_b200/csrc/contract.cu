@@ -711,7 +711,7 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 // Default: left-over columns are padded onto the tensor pipe (all-DMMA).  SPEIGEN_HYBRID_DFMA=1 selects the
-// <NTF, RF=4> variant with dedicated DFMA warps instead.  Measured on B200 (tools/dev_ab.py, same process, same thermal
+// <NTF, RF=4> variant with dedicated DFMA warps instead.  Measured on B200 (tools/k1_probe.py ab, same process, same thermal
 // state, m=50k q=20): all-DMMA 4.24 ms vs hybrid 4.54 ms per launch in the sustained, power-capped regime - DFMA
 // costs more energy per flop than DMMA, so doing 17 % fewer flops on the same datapath does not pay.  Read per launch
 // so a harness can A/B inside one process.

@@ -46,7 +46,8 @@ void load() {
 const NcclApi* nccl_api() {
   std::call_once(g_once, load);
   if (!g_ok) {
-    set_error("NCCL (libnccl.so.2) could not be loaded: %s", dlerror() ? dlerror() : "symbol lookup failed");
+    const char* why = dlerror();   // dlerror() clears its state: read it once
+    set_error("NCCL (libnccl.so.2) could not be loaded: %s", why ? why : "symbol lookup failed");
     return nullptr;
   }
   return &g_api;

@@ -1,4 +1,4 @@
-"""Times the dense FP64 tensor-core GEMM on resident random operands:  python tools/dev_gemm.py M N K [symmetric] [reps]"""
+"""Times the dense FP64 tensor-core GEMM on resident random operands:  python tools/gemm_rates.py M N K [symmetric] [reps]"""
 import os
 import sys
 
