@@ -35,6 +35,11 @@ extern "C" {
 #define SPEIGEN_ERR_ARG 23
 #define SPEIGEN_ERR_NOMEM 24
 #define SPEIGEN_ERR_UNSUPPORTED 25
+#define SPEIGEN_ERR_NUMERIC 26        /* a Procrustes target (G - H, R/spEigen.R:180) was rank deficient or non-finite: the reference's
+                                         svd() would return an arbitrary completion; this library refuses instead of returning it */
+#define SPEIGEN_ERR_NOT_CONVERGED 27  /* the block subspace iteration that replaces eigen()/svd() (R/spEigen.R:68,76) did not reach
+                                         init_tol within init_max_passes */
+#define SPEIGEN_ERR_TIMEOUT 28        /* a GPU waited longer than exchange_timeout_ms for a peer in the fused exchange */
 
 /* ---- configuration: the constants the reference hard-codes, plus device options ---------------- */
 typedef struct speigen_cfg {
@@ -63,6 +68,9 @@ typedef struct speigen_cfg {
                                 (R/spEigen.R:77 tests the full spectrum; a Ritz value < pd_tol proves S is not PD) */
   int32_t p2p_exchange;      /* 1: row-sharded covariance exchanges its m x q row blocks with peer-memory stores fused into the
                                 contraction epilogue (NVLink P2P / CUDA IPC); 0: NCCL allgather after the kernel */
+  int32_t exchange_timeout_ms;   /* 10000: bound on every device-side wait for a peer (fused exchange flags); on expiry the call
+                                    returns SPEIGEN_ERR_TIMEOUT instead of hanging the other GPUs */
+  int32_t allow_unconverged_init;   /* 0: an initialiser that misses init_tol is an error (SPEIGEN_ERR_NOT_CONVERGED) */
 } speigen_cfg;
 
 void speigen_cfg_default(speigen_cfg* cfg);
@@ -179,6 +187,10 @@ int speigen_solver_load_device_rows(speigen_solver* s, int32_t local_idx, int64_
 int speigen_solver_mm_steps(speigen_solver* s, int32_t nsteps, int32_t stage, double rho, const double* d_or_null,
                             float* ms_out);
 int speigen_solver_sync(speigen_solver* s);
+/* Diagnostics of the last fused tail kernel (device 0): out48[0] SQUAREM step a, [1] ||R||, [2] ||U||, [3] Gram passes, [4] Jacobi
+ * sweeps, [7] number of clock stamps, [8..] phase clock of CTA 0 in ns since kernel entry (produce, then per pass: Gram, exchange,
+ * solve, apply).  Measurement side channel only. */
+int speigen_solver_tail_diag(speigen_solver* s, double* out48);
 /* 0: single GPU (no exchange), 1: NCCL collectives, 2: fused peer-store exchange (valid after speigen_solver_init_comm) */
 int speigen_solver_exchange_mode(speigen_solver* s);
 /* CUDA-event timing of the contraction kernel launches of local device 0 (for the roofline line of bench.py). */

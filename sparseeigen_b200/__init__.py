@@ -43,6 +43,7 @@ class Cfg(C.Structure):
         ("max_backtracks", C.c_int32), ("init_max_passes", C.c_int32), ("init_tol", C.c_double),
         ("init_block", C.c_int32), ("init_seed", C.c_uint64), ("check_symmetric", C.c_int32), ("check_na", C.c_int32),
         ("n_gpus", C.c_int32), ("first_device", C.c_int32), ("fused_epilogue", C.c_int32), ("verbose", C.c_int32), ("pd_check_passes", C.c_int32), ("p2p_exchange", C.c_int32),
+        ("exchange_timeout_ms", C.c_int32), ("allow_unconverged_init", C.c_int32),
     ]
 
 
@@ -135,6 +136,7 @@ def lib():
     L.speigen_solver_load_device_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]
     L.speigen_solver_mm_steps.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, _dp, C.POINTER(C.c_float)]
     L.speigen_solver_sync.argtypes = [C.c_void_p]
+    L.speigen_solver_tail_diag.argtypes = [C.c_void_p, _dp]
     L.speigen_solver_exchange_mode.argtypes = [C.c_void_p]
     L.speigen_solver_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
     L.speigen_solver_kernel_time.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int32)]
@@ -612,6 +614,15 @@ class Solver:
 
     def sync(self):
         _check(self.L.speigen_solver_sync(self.h))
+
+    def tail_diag(self):
+        """Diagnostics of the last fused tail kernel on device 0 (passes, Jacobi sweeps, CTA 0's phase clock in microseconds)."""
+        out = np.zeros(48)
+        _check(self.L.speigen_solver_tail_diag(self.h, _ptr(out)))
+        n = int(out[7])
+        return dict(a=out[0], nR=out[1], nU=out[2], passes=int(out[3]), sweeps=int(out[4]),
+                    clock_us=[float(x) for x in np.round(out[8:8 + n] * 1e-3, 2)],
+                    jacobi_us=dict(setup=float((out[42] - out[41]) * 1e-3), sweeps=float((out[40] - out[42]) * 1e-3)))
 
     def kernel_timing(self, enable=True):
         _check(self.L.speigen_solver_kernel_timing(self.h, 1 if enable else 0))

@@ -56,6 +56,8 @@ void speigen_cfg_default(speigen_cfg* c) {
   c->verbose = 0;
   c->pd_check_passes = 4;
   c->p2p_exchange = 1;
+  c->exchange_timeout_ms = 10000;
+  c->allow_unconverged_init = 0;
 }
 
 const char* speigen_last_error(void) { return last_error(); }
@@ -212,13 +214,27 @@ int speigen_solver_contract(speigen_solver* s, const double* U_host, int32_t nco
   return S.op_download_panel(BZ, pd, Y_host);
 }
 
+// status of the tail kernels after a kernel-level call (sticky device flag -> error code)
+static int tail_status(Solver& S) {
+  API_TRY(S.sync_all());
+  int st = 0;
+  Dev& d = S.devs[0];
+  cudaSetDevice(d.ordinal);
+  SPE_CUDA(cudaMemcpy(&st, d.tstatus, sizeof(int), cudaMemcpyDeviceToHost));
+  return S.check_tail_status(static_cast<double>(st));
+}
+
 int speigen_solver_polar(speigen_solver* s, const double* A_host, int32_t ncols, double* U_host) {
   DeviceRestore restore_device__;
   Solver& S = s->impl;
   if (ncols < 1 || ncols > S.bq) { set_error("polar: ncols %d outside 1..%d", ncols, S.bq); return SPEIGEN_ERR_ARG; }
   const PanelDims pd = make_dims(S.m, ncols, S.cplx);
   API_TRY(S.op_upload_panel(A_host, BQ, pd));
-  API_TRY(S.op_polar(BQ, BZ, pd, false, nullptr, 0));
+  TailSpec ts;                       // the fused polar tail (K3): Gram passes + Jacobi/Taylor + applies in one kernel
+  ts.producer = TAIL_PANEL; ts.T = BQ; ts.out = BZ; ts.out_all = true;
+  API_TRY(S.op_tail(ts, pd, make_stage(0.1, 0.1)));
+  API_TRY(S.wait_latest_tail());
+  API_TRY(tail_status(S));
   return S.op_download_panel(BZ, pd, U_host);
 }
 
@@ -231,22 +247,23 @@ int speigen_solver_mm_update(speigen_solver* s, const double* V_host, const doub
   const StageConsts sc = make_stage(p, eps);
   API_TRY(S.op_upload_panel(V_host, BV, pd));
   API_TRY(S.set_qvecs(d, rho_vec));
-  for (Dev& dv : S.devs) {
-    cudaSetDevice(dv.ordinal);
-    API_TRY(launch_absmin(pd, dv.buf[BV], dv.absmin_a, dv.ps.ticket, dv.st));
-    dv.wmax = const_cast<double*>(absmin_final(dv.absmin_a));
+  {
+    TailSpec ts;   // column minima of V (the weights' column max, R/spEigen.R:176)
+    ts.T = BV; ts.out = BV; ts.skip_polar = true; ts.absmin = true;
+    API_TRY(S.op_tail(ts, pd, sc));
   }
-  if (fused) {
-    API_TRY(S.op_contract(BV, pd, NBUF, BB, BV, false, sc));
-    API_TRY(S.op_polar(BB, BV1, pd, false, nullptr, 0));
+  TailSpec ts;
+  ts.T = BB; ts.out = BV1; ts.out_all = true; ts.absmin = true;   // cold Jacobi start: the result does not depend on earlier calls
+  if (fused && !(S.data && S.prob.world > 1)) {
+    API_TRY(S.op_contract_loop(BV, pd, NBUF, BB, BV, false, sc));
+    ts.producer = TAIL_PANEL;
   } else {
-    API_TRY(S.op_contract(BV, pd, BY, NBUF, NBUF, false, sc));
-    for (Dev& dv : S.devs) {
-      cudaSetDevice(dv.ordinal);
-      API_TRY(launch_reweight(pd, dv.buf[BY], dv.buf[BV], dv.dvec, dv.rho, dv.wmax, sc, dv.buf[BB], dv.ps.gram_part, dv.st));
-    }
-    API_TRY(S.op_polar(BB, BV1, pd, true, nullptr, 0));
+    API_TRY(S.op_contract_loop(BV, pd, BY, NBUF, NBUF, false, sc));
+    ts.producer = TAIL_REWEIGHT; ts.in0 = BY; ts.in1 = BV; ts.use_prev = true;
   }
+  API_TRY(S.op_tail(ts, pd, sc));
+  API_TRY(S.wait_latest_tail());
+  API_TRY(tail_status(S));
   return S.op_download_panel(BV1, pd, V1_host);
 }
 
@@ -259,13 +276,15 @@ int speigen_solver_objective(speigen_solver* s, const double* V_host, const doub
   const StageConsts sc = make_stage(p, eps);
   API_TRY(S.op_upload_panel(V_host, BV0, pd));
   API_TRY(S.set_qvecs(d, rho_vec));
-  API_TRY(S.op_contract(BV0, pd, BY0, NBUF, BV0, true, sc));
-  for (Dev& dv : S.devs) {
-    cudaSetDevice(dv.ordinal);
-    API_TRY(launch_objective(pd, dv.buf[BV0], sc, dv.dots_part, S.n_dot_parts, dv.dvec, dv.rho, dv.ps, dv.scal + 8, dv.st));
+  {
+    TailSpec ts;   // penalty column sums of V0 (R/spEigen.R:133-134)
+    ts.T = BV0; ts.out = BV0; ts.skip_polar = true; ts.absmin = true; ts.gsum = true;
+    API_TRY(S.op_tail(ts, pd, sc));
   }
-  API_TRY(S.read_scalars(9 + 2 * pd.q));
-  *F_out = S.h_scal[8];
+  API_TRY(S.op_contract_loop(BV0, pd, BY0, NBUF, BV0, true, sc));
+  API_TRY(S.op_finish_objective(pd));
+  API_TRY(tail_status(S));
+  *F_out = S.h_res[0];
   return SPEIGEN_OK;
 }
 
@@ -326,6 +345,15 @@ int speigen_solver_load_device_rows(speigen_solver* s, int32_t li, int64_t row0,
 int speigen_solver_mm_steps(speigen_solver* s, int32_t nsteps, int32_t stage, double rho, const double* d, float* ms_out) {
   DeviceRestore restore_device__;
   return s->impl.mm_steps(nsteps, stage, rho, d, ms_out);
+}
+int speigen_solver_tail_diag(speigen_solver* s, double* out48) {
+  DeviceRestore restore_device__;
+  if (!s || !out48) return SPEIGEN_ERR_ARG;
+  API_TRY(s->impl.sync_all());
+  Dev& d = s->impl.devs[0];
+  cudaSetDevice(d.ordinal);
+  SPE_CUDA(cudaMemcpy(out48, d.tdiag, 48 * sizeof(double), cudaMemcpyDeviceToHost));
+  return SPEIGEN_OK;
 }
 int speigen_solver_sync(speigen_solver* s) {
   DeviceRestore restore_device__; return s->impl.sync_all(); }

@@ -112,7 +112,17 @@ struct StageConsts {
 };
 #ifdef __CUDACC__
 __host__ __device__ inline double weight_of_abs(double a, const StageConsts& sc) {
-  return (a > sc.eps) ? sc.half_over_c1 / (a * a + sc.p * a) : sc.w0;   // R/spEigen.R:170-173
+#ifdef __CUDA_ARCH__
+  // rounding sequence pinned (no compiler-chosen FMA contraction): every kernel derives the same weight from the same |V|
+  return (a > sc.eps) ? __ddiv_rn(sc.half_over_c1, __fma_rn(a, a, __dmul_rn(sc.p, a))) : sc.w0;   // R/spEigen.R:170-173
+#else
+  return (a > sc.eps) ? sc.half_over_c1 / (a * a + sc.p * a) : sc.w0;
+#endif
+}
+// One component of B = d*Y - (w(|V|) - wmax) * V * rho (R/spEigen.R:176-177, G - H) with the rounding sequence pinned, so
+// that the contraction's fused epilogue and the tail's producer give the same bits whatever the compiler contracts.
+__device__ __forceinline__ double reweight_elem(double y, double v, double w_minus_wmax, double d, double rho) {
+  return __fma_rn(d, y, -__dmul_rn(__dmul_rn(w_minus_wmax, v), rho));
 }
 #endif
 

@@ -18,6 +18,7 @@
 //
 // Replaces: R/spEigen.R:177 (G), :136/:138 (X %*% V0) of the reference (base-R dgemm/zgemm).
 #include "contract.cuh"
+#include "tail.cuh"
 #include "../../include/speigen_b200.h"
 #include <cstdlib>
 
@@ -57,12 +58,10 @@ __device__ __forceinline__ void epi_pair(const KParams& prm, const double* s_d, 
   if (jl >= prm.rows || c0 >= prm.ncr) return;
   const size_t roff = static_cast<size_t>(ep.row_off + jl) * ep.pitch;
   const bool has1 = (c0 + 1) < prm.ncr;
-  if (ep.npeers > 0) {
-    if (ep.peerY[0]) {
-      for (int p = 0; p < ep.npeers; ++p) {
-        if (has1) *reinterpret_cast<double2*>(ep.peerY[p] + roff + c0) = make_double2(y0, y1);
-        else ep.peerY[p][roff + c0] = y0;
-      }
+  if (ep.npeers > 0 && ep.peerY[0]) {
+    for (int p = 0; p < ep.npeers; ++p) {
+      if (has1) *reinterpret_cast<double2*>(ep.peerY[p] + roff + c0) = make_double2(y0, y1);
+      else ep.peerY[p][roff + c0] = y0;
     }
   } else if (ep.Y) {
     if (has1) *reinterpret_cast<double2*>(ep.Y + roff + c0) = make_double2(y0, y1);
@@ -76,21 +75,21 @@ __device__ __forceinline__ void epi_pair(const KParams& prm, const double* s_d, 
     const int cc = c0 >> 1;
     if (ep.B || ep.peerB[0]) {
       const double t = weight_of_abs(hypot(v0, v1), ep.sc) - s_wmax[cc];
-      const double2 bb = make_double2(s_d[cc] * y0 - t * v0 * s_rho[cc], s_d[cc] * y1 - t * v1 * s_rho[cc]);
-      if (ep.npeers > 0) { for (int p = 0; p < ep.npeers; ++p) *reinterpret_cast<double2*>(ep.peerB[p] + roff + c0) = bb; }
+      const double2 bb = make_double2(reweight_elem(y0, v0, t, s_d[cc], s_rho[cc]), reweight_elem(y1, v1, t, s_d[cc], s_rho[cc]));
+      if (ep.npeers > 0 && ep.peerB[0]) { for (int p = 0; p < ep.npeers; ++p) *reinterpret_cast<double2*>(ep.peerB[p] + roff + c0) = bb; }
       else *reinterpret_cast<double2*>(ep.B + roff + c0) = bb;
     }
     ds0 += v0 * y0 + v1 * y1;
   } else {
     if (ep.B || ep.peerB[0]) {
       const double t0 = weight_of_abs(fabs(v0), ep.sc) - s_wmax[c0];
-      const double b0 = s_d[c0] * y0 - t0 * v0 * s_rho[c0];
+      const double b0 = reweight_elem(y0, v0, t0, s_d[c0], s_rho[c0]);
       double b1 = 0.0;
       if (has1) {
         const double t1 = weight_of_abs(fabs(v1), ep.sc) - s_wmax[c0 + 1];
-        b1 = s_d[c0 + 1] * y1 - t1 * v1 * s_rho[c0 + 1];
+        b1 = reweight_elem(y1, v1, t1, s_d[c0 + 1], s_rho[c0 + 1]);
       }
-      if (ep.npeers > 0) {
+      if (ep.npeers > 0 && ep.peerB[0]) {
         for (int p = 0; p < ep.npeers; ++p) {
           if (has1) *reinterpret_cast<double2*>(ep.peerB[p] + roff + c0) = make_double2(b0, b1);
           else ep.peerB[p][roff + c0] = b0;
@@ -138,13 +137,29 @@ k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
     }
     mbar_fence_init();
   }
+  if (prm.epi.wait_flags) {
+    // row-sharded MM loop: the operand panel's rows and the column minima arrive from the peers' tail kernels
+    if (threadIdx.x < prm.epi.wait_n)
+      spin_until_ge(prm.epi.wait_flags + threadIdx.x * kFlagStride, prm.epi.wait_epoch, prm.epi.spin_budget_ns, prm.epi.status,
+                    prm.epi.wait_n > 1);
+    __syncthreads();
+    asm volatile("fence.proxy.async.global;" ::: "memory");   // peer (generic-proxy) stores -> this CTA's bulk/TMA loads
+  }
   if (threadIdx.x < kMaxCols) {
     const int c = threadIdx.x;
     const bool ok = c < prm.epi.q;
     s_d[c] = (ok && prm.epi.d) ? prm.epi.d[c] : 1.0;
     s_rho[c] = (ok && prm.epi.rho) ? prm.epi.rho[c] : 0.0;
     // epi.wmax carries min_j |V[j,c]|; the column max of the weights is w(min) (w is non-increasing)   R/spEigen.R:176
-    s_wmax[c] = (ok && prm.epi.wmax) ? weight_of_abs(prm.epi.wmax[c], prm.epi.sc) : 0.0;
+    double wm = 0.0;
+    if (ok && prm.epi.stat_absmin) {
+      double v = 1.7976931348623157e308;
+      for (int r = 0; r < prm.epi.stat_n; ++r) v = fmin(v, __ldcv(prm.epi.stat_absmin + static_cast<size_t>(r) * prm.epi.stat_stride + c));
+      wm = weight_of_abs(v, prm.epi.sc);
+    } else if (ok && prm.epi.wmax) {
+      wm = weight_of_abs(prm.epi.wmax[c], prm.epi.sc);
+    }
+    s_wmax[c] = wm;
   }
   __syncthreads();
 
@@ -242,7 +257,7 @@ k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
     named_bar_sync(1, NCW * 32);
     if (ctid < prm.epi.npeers) {
       __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(prm.epi.peer_flag[ctid] + prm.epi.my_shard) = prm.epi.epoch;
+      st_release_sys_u64(prm.epi.peer_flag[ctid] + prm.epi.my_shard, prm.epi.epoch);
     }
   };
 
@@ -489,11 +504,8 @@ k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
 __global__ void __launch_bounds__(256) k_exchange_wait_copy(const unsigned long long* flags, int world, unsigned long long epoch,
                                                             const double* srcY, double* dstY, const double* srcB, double* dstB,
                                                             size_t panel_doubles, const double* src_dots, double* dst_dots,
-                                                            int ndots) {
-  if (threadIdx.x < world) {
-    const volatile unsigned long long* f = flags + threadIdx.x;
-    while (*f < epoch) { __nanosleep(64); }
-  }
+                                                            int ndots, int* status, long long budget_ns) {
+  if (threadIdx.x < world) spin_until_ge(flags + threadIdx.x, epoch, budget_ns, status, true);
   __syncthreads();
   __threadfence_system();
   const size_t n2 = panel_doubles / 2;
@@ -865,8 +877,9 @@ int launch_contract_std(const StreamMat& A, const double* P, int ncr, const EpiA
 
 int launch_exchange_wait_copy(const unsigned long long* flags, int world, unsigned long long epoch, const double* srcY,
                               double* dstY, const double* srcB, double* dstB, size_t panel_doubles, const double* src_dots,
-                              double* dst_dots, int ndots, cudaStream_t stream) {
-  k_exchange_wait_copy<<<148, 256, 0, stream>>>(flags, world, epoch, srcY, dstY, srcB, dstB, panel_doubles, src_dots, dst_dots, ndots);
+                              double* dst_dots, int ndots, int* status, long long budget_ns, cudaStream_t stream) {
+  k_exchange_wait_copy<<<148, 256, 0, stream>>>(flags, world, epoch, srcY, dstY, srcB, dstB, panel_doubles, src_dots, dst_dots, ndots,
+                                                status, budget_ns);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

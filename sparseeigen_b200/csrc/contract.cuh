@@ -44,6 +44,16 @@ struct EpiArgs {
   unsigned long long* peer_flag[8] = {};   // [world] epoch flags on each GPU
   unsigned long long epoch = 0;
   int* done_count = nullptr;       // CTA completion counter (self-resetting)
+  // ---- row-sharded MM loop (round 2): the operand panel is assembled in place by the peers' tail kernels (tail.cuh), which
+  // also publish the column minima of |V|.  The kernel waits for their epoch flags before it touches either.
+  const unsigned long long* wait_flags = nullptr;   // own mailbox stat_flag (stride kFlagStride)
+  int wait_n = 0;
+  unsigned long long wait_epoch = 0;
+  const double* stat_absmin = nullptr;   // [stat_n][stat_stride] column minima of |V| per rank (overrides wmax)
+  int stat_n = 0;
+  int stat_stride = 0;
+  int* status = nullptr;           // bit 2: exchange wait timed out
+  long long spin_budget_ns = 10000000000ll;
 };
 
 struct ContractWorkspace {
@@ -80,6 +90,6 @@ size_t contract_tr_workspace_slots(int64_t kd, int num_sms);
 // (panel rows [0, rows) and the per-rank dot sums) into their destination buffers.
 int launch_exchange_wait_copy(const unsigned long long* flags, int world, unsigned long long epoch, const double* srcY,
                               double* dstY, const double* srcB, double* dstB, size_t panel_doubles, const double* src_dots,
-                              double* dst_dots, int ndots, cudaStream_t stream);
+                              double* dst_dots, int ndots, int* status, long long budget_ns, cudaStream_t stream);
 
 }  // namespace speigen

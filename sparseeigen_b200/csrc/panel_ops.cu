@@ -276,12 +276,12 @@ __global__ void __launch_bounds__(256) k_reweight(const double* Y, const double*
       const double2 v = *reinterpret_cast<const double2*>(V + g);
       const double2 y = *reinterpret_cast<const double2*>(Y + g);
       const double tt = weight_of_abs(hypot(v.x, v.y), sc) - s_w[c];
-      *reinterpret_cast<double2*>(B + g) = make_double2(s_d[c] * y.x - tt * v.x * s_rho[c], s_d[c] * y.y - tt * v.y * s_rho[c]);
+      *reinterpret_cast<double2*>(B + g) = make_double2(reweight_elem(y.x, v.x, tt, s_d[c], s_rho[c]), reweight_elem(y.y, v.y, tt, s_d[c], s_rho[c]));
     } else {
       const size_t g = static_cast<size_t>(r) * pitch + c;
       const double v = V[g], y = Y[g];
       const double tt = weight_of_abs(fabs(v), sc) - s_w[c];
-      B[g] = s_d[c] * y - tt * v * s_rho[c];
+      B[g] = reweight_elem(y, v, tt, s_d[c], s_rho[c]);
     }
   }
 }

@@ -112,6 +112,14 @@ int Solver::create(const speigen_problem* p, const speigen_cfg* c) {
   }
   SPE_CUDA(cudaSetDevice(devs[0].ordinal));
   SPE_CUDA(cudaMallocHost(&h_scal, 512 * sizeof(double)));
+  // result block of the MM loop: written by k_finish_objective straight into mapped pinned memory (no copy on the critical path)
+  SPE_CUDA(cudaHostAlloc(&h_res, 512 * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
+  std::memset(h_res, 0, 512 * sizeof(double));
+  SPE_CUDA(cudaHostGetDevicePointer(&devs[0].res_host_dev, h_res, 0));
+  if (prob.world == 1) {
+    Dev& d0 = devs[0];
+    d0.peer_arena[0] = static_cast<char*>(d0.arena);
+  }
   return SPEIGEN_OK;
 }
 
@@ -140,7 +148,18 @@ int Solver::alloc_dev(Dev& d) {
   const size_t pbytes = static_cast<size_t>(mrows) * pdb.pitch * sizeof(double);
   std::vector<std::pair<void**, size_t>> req;
   auto want = [&](auto** p, size_t bytes) { req.emplace_back(reinterpret_cast<void**>(p), (bytes + 255) / 256 * 256); };
+  // peer-visible head of the arena: panels, then the mailbox - sizes depend on global parameters only, so the offsets are the
+  // same on every rank and a peer's copy of panel b is peer_arena[r] + off_buf[b]
   for (int bb = 0; bb < NBUF; ++bb) want(&d.buf[bb], pbytes);
+  want(&d.mail, sizeof(Mailbox));
+  want(&d.cta_part, static_cast<size_t>(d.num_sms) * kTriMax * sizeof(double));
+  want(&d.cta_stat, static_cast<size_t>(d.num_sms) * kStatLen * sizeof(double));
+  want(&d.tail_ticket, 4 * sizeof(int));
+  want(&d.gram_epoch, sizeof(unsigned long long));
+  want(&d.a_cur, sizeof(double));
+  want(&d.tdiag, 48 * sizeof(double));
+  want(&d.tstatus, sizeof(int));
+  want(&d.twarm, static_cast<size_t>(N_TAIL_SITES) * 2 * kWarmDoubles * sizeof(double));
   if (cplx && !data) want(&d.hat, 2 * pbytes);
   if (data) {
     want(&d.Tdata, static_cast<size_t>(padded_rows(std::max<int64_t>(d.a_kd, 1))) * pdb.pitch * sizeof(double));
@@ -191,6 +210,9 @@ int Solver::alloc_dev(Dev& d) {
   SPE_CUDA(cudaMemsetAsync(d.arena, 0, total, d.st));
   size_t off = 0;
   for (auto& r : req) { *r.first = static_cast<char*>(d.arena) + off; off += r.second; }
+  for (int bb = 0; bb < NBUF; ++bb) d.off_buf[bb] = reinterpret_cast<char*>(d.buf[bb]) - static_cast<char*>(d.arena);
+  d.off_mail = reinterpret_cast<char*>(d.mail) - static_cast<char*>(d.arena);
+  SPE_TRY(tail_prepare_device());   // load the module / set attributes now: later launches must never block behind a spinning peer
   if (!data && prob.world > 1 && prob.world <= kMaxPeers) {   // separate allocations: exported with cudaIpcGetMemHandle
     const size_t xb_bytes = 4 * pbytes;
     SPE_CUDA(cudaMalloc(&d.xb, xb_bytes));
@@ -218,6 +240,8 @@ void Solver::destroy() {
   devs.clear();
   if (h_scal) cudaFreeHost(h_scal);
   h_scal = nullptr;
+  if (h_res) cudaFreeHost(h_res);
+  h_res = nullptr;
 }
 
 void Solver::reset_for_reuse() {
@@ -245,6 +269,7 @@ int Solver::init_comm_all() {
   // (ncclCommInitAll costs hundreds of milliseconds, more than the whole solve at m = 50k on 8 GPUs).
   SPE_TRY(init_p2p());
   if (p2p && !data) { comm_ready = true; return SPEIGEN_OK; }
+  const bool had_peers = peer_ok;
   const NcclApi* nc = nccl_api();
   if (!nc) return SPEIGEN_ERR_NCCL;
   std::vector<int> ords;
@@ -253,6 +278,7 @@ int Solver::init_comm_all() {
   SPE_NCCL(nc->CommInitAll(comms.data(), static_cast<int>(devs.size()), ords.data()));
   for (size_t i = 0; i < devs.size(); ++i) devs[i].comm = comms[i];
   comm_ready = true;
+  (void)had_peers;
   return init_p2p();
 }
 
@@ -276,8 +302,11 @@ int Solver::init_comm_rank(const void* id128) {
 // handles (allgathered over the NCCL communicator) across processes.  Any failure leaves the NCCL allgather path on.
 int Solver::init_p2p() {
   p2p = false;
-  if (prob.world <= 1 || data || !cfg.p2p_exchange || prob.world > kMaxPeers) return SPEIGEN_OK;
-  if (rows_per_shard * (prob.world - 1) >= m) return SPEIGEN_OK;   // an empty shard would never raise its flag
+  peer_ok = false;
+  if (prob.world <= 1 || data || prob.world > kMaxPeers) return SPEIGEN_OK;
+  // the fused exchange needs every shard non-empty (an empty one would never raise its flag); the peer mappings alone
+  // (symmetry scan across shards) do not
+  const bool want_p2p = cfg.p2p_exchange && !(rows_per_shard * (prob.world - 1) >= m);
   const bool single_process = static_cast<int>(devs.size()) == prob.world;
   if (single_process) {
     for (Dev& a : devs) {
@@ -293,9 +322,12 @@ int Solver::init_p2p() {
         a.peer_xb[b.shard] = b.xb;
         a.peer_xdots[b.shard] = b.xdots;
         a.peer_xflags[b.shard] = b.xflags;
+        a.peer_arena[b.shard] = static_cast<char*>(b.arena);
+        a.peer_A[b.shard] = b.A;
       }
     }
-    p2p = true;
+    peer_ok = true;
+    p2p = want_p2p;
     return SPEIGEN_OK;
   }
   // one process per GPU: exchange IPC handles through the communicator (3 handles of 64 bytes per rank)
@@ -303,30 +335,38 @@ int Solver::init_p2p() {
   if (!nc || devs.size() != 1) return SPEIGEN_OK;
   Dev& d = devs[0];
   SPE_CUDA(cudaSetDevice(d.ordinal));
-  cudaIpcMemHandle_t mine[3];
+  constexpr int NH = 5;   // xb, xdots, xflags, arena (panels + mailbox), A (matrix shard: symmetry scan)
+  cudaIpcMemHandle_t mine[NH];
   if (cudaIpcGetMemHandle(&mine[0], d.xb) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], d.xdots) != cudaSuccess ||
-      cudaIpcGetMemHandle(&mine[2], d.xflags) != cudaSuccess) { cudaGetLastError(); return SPEIGEN_OK; }
+      cudaIpcGetMemHandle(&mine[2], d.xflags) != cudaSuccess || cudaIpcGetMemHandle(&mine[3], d.arena) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine[4], d.A) != cudaSuccess) { cudaGetLastError(); return SPEIGEN_OK; }
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
-  const size_t per = 3 * 64 / sizeof(double);
+  const size_t per = NH * 64 / sizeof(double);
   double* dev_h = nullptr;
   SPE_CUDA(cudaMalloc(&dev_h, per * prob.world * sizeof(double)));
-  SPE_CUDA(cudaMemcpyAsync(dev_h + per * d.shard, mine, 3 * 64, cudaMemcpyHostToDevice, d.st));
+  SPE_CUDA(cudaMemcpyAsync(dev_h + per * d.shard, mine, NH * 64, cudaMemcpyHostToDevice, d.st));
   SPE_NCCL(nc->AllGather(dev_h + per * d.shard, dev_h, per, NCCL_DOUBLE, d.comm, d.st));
-  std::vector<cudaIpcMemHandle_t> all(3 * prob.world);
-  SPE_CUDA(cudaMemcpyAsync(all.data(), dev_h, 3 * 64 * prob.world, cudaMemcpyDeviceToHost, d.st));
+  std::vector<cudaIpcMemHandle_t> all(NH * prob.world);
+  SPE_CUDA(cudaMemcpyAsync(all.data(), dev_h, NH * 64 * prob.world, cudaMemcpyDeviceToHost, d.st));
   SPE_CUDA(cudaStreamSynchronize(d.st));
   cudaFree(dev_h);
   bool ok = true;
   for (int r = 0; r < prob.world && ok; ++r) {
-    if (r == d.shard) { d.peer_xb[r] = d.xb; d.peer_xdots[r] = d.xdots; d.peer_xflags[r] = d.xflags; continue; }
-    void* ptr[3] = {nullptr, nullptr, nullptr};
-    for (int k = 0; k < 3 && ok; ++k) {
-      if (cudaIpcOpenMemHandle(&ptr[k], all[3 * r + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    if (r == d.shard) {
+      d.peer_xb[r] = d.xb; d.peer_xdots[r] = d.xdots; d.peer_xflags[r] = d.xflags;
+      d.peer_arena[r] = static_cast<char*>(d.arena); d.peer_A[r] = d.A;
+      continue;
+    }
+    void* ptr[NH] = {};
+    for (int k = 0; k < NH && ok; ++k) {
+      if (cudaIpcOpenMemHandle(&ptr[k], all[NH * r + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
       d.ipc_opened[d.n_ipc_opened++] = ptr[k];
     }
     d.peer_xb[r] = static_cast<double*>(ptr[0]);
     d.peer_xdots[r] = static_cast<double*>(ptr[1]);
     d.peer_xflags[r] = static_cast<unsigned long long*>(ptr[2]);
+    d.peer_arena[r] = static_cast<char*>(ptr[3]);
+    d.peer_A[r] = static_cast<const double*>(ptr[4]);
   }
   // every rank must agree, otherwise some would wait for flags that never come
   double agree = ok ? 1.0 : 0.0;
@@ -337,7 +377,8 @@ int Solver::init_p2p() {
   SPE_CUDA(cudaMemcpyAsync(&agree, dflag, sizeof(double), cudaMemcpyDeviceToHost, d.st));
   SPE_CUDA(cudaStreamSynchronize(d.st));
   cudaFree(dflag);
-  p2p = (agree == static_cast<double>(prob.world));
+  peer_ok = (agree == static_cast<double>(prob.world));
+  p2p = peer_ok && want_p2p;
   return SPEIGEN_OK;
 }
 
@@ -407,21 +448,30 @@ int Solver::prepare() {
   }
   SPE_TRY(build_tensor_maps());
   if (!data) {
-    // isSymmetric.matrix needs S[i,j] next to S[j,i]: possible on one GPU, and on several GPUs of ONE process when peer
-    // access is up (the transposed tile is read from the shard that owns it); one-process-per-GPU runs trust the caller.
+    // isSymmetric.matrix needs S[i,j] next to S[j,i]: the transposed tile is read from the shard that owns it - the own one on
+    // one GPU, a peer's over NVLink otherwise (peer access inside one process, CUDA IPC mappings across processes).  Without
+    // peer mappings the check cannot be honoured: refuse rather than silently contract S^T (check_symmetric = 0 trusts the caller).
     const bool single_process = static_cast<int>(devs.size()) == prob.world;
-    const bool can_check = prob.world == 1 || (single_process && p2p);
+    const bool can_check = prob.world == 1 || peer_ok;
+    if (cfg.check_symmetric && !can_check) {
+      set_error("isSymmetric(S) cannot be verified without peer access between the GPUs (p2p exchange unavailable); "
+                "pass check_symmetric = 0 to trust the caller");
+      return SPEIGEN_ERR_UNSUPPORTED;
+    }
     const int full = (can_check && (cfg.check_symmetric || cfg.check_na)) ? 1 : 0;
-    std::vector<const double*> shard_ptrs(prob.world, nullptr);
-    if (single_process) for (Dev& d : devs) shard_ptrs[d.shard] = d.A;
     for (Dev& d : devs) {
       SPE_CUDA(cudaSetDevice(d.ordinal));
+      std::vector<const double*> shard_ptrs(prob.world, nullptr);
+      for (int r = 0; r < prob.world; ++r) shard_ptrs[r] = (prob.world == 1) ? d.A : d.peer_A[r];
       SPE_TRY(launch_scan_cov(d.A, d.a_rows, m, d.a_ld, d.lo, cplx, full, prob.world > 1 ? shard_ptrs.data() : nullptr,
                               prob.world, rows_per_shard, d.scan_part, d.ps.ticket, d.scal, d.st));
     }
     if (prob.world > 1 && devs[0].comm) {
       SPE_NCCL(nc->GroupStart());
       for (Dev& d : devs) {
+        if (!single_process) {
+          SPE_NCCL(nc->AllReduce(d.scal + 0, d.scal + 0, 2, NCCL_DOUBLE, NCCL_SUM, d.comm, d.st));
+        }
         SPE_NCCL(nc->AllReduce(d.scal + 2, d.scal + 2, 1, NCCL_DOUBLE, NCCL_MAX, d.comm, d.st));
         SPE_NCCL(nc->AllReduce(d.scal + 3, d.scal + 3, 1, NCCL_DOUBLE, NCCL_SUM, d.comm, d.st));
       }
@@ -613,7 +663,8 @@ int Solver::op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vep
       SPE_TRY(launch_exchange_wait_copy(d.xflags, prob.world, epoch, sy, want_y ? d.buf[outY] : nullptr, sb,
                                         want_b ? d.buf[outB] : nullptr, std::max(nd, static_cast<size_t>(rows_per_shard) * prob.world * pd.pitch),
                                         want_dots ? d.xdots + static_cast<size_t>(parity) * prob.world * kMaxCols : nullptr,
-                                        d.dots_part, prob.world * nout, d.st));
+                                        d.dots_part, prob.world * nout, d.tstatus,
+                                        static_cast<long long>(cfg.exchange_timeout_ms > 0 ? cfg.exchange_timeout_ms : 10000) * 1000000ll, d.st));
     }
     if (want_dots) n_dot_parts = prob.world;
     return SPEIGEN_OK;
@@ -671,6 +722,168 @@ int Solver::op_polar(Buf in, Buf out, const PanelDims& pd, bool have_gram, doubl
     SPE_TRY(launch_apply(pd, d.buf[BT2], d.Msmall, d.buf[out], nullptr, am, d.ps.ticket, d.st));
   }
   return SPEIGEN_OK;
+}
+
+// ---- round 2: fused, row-sharded tail + MM-loop contraction ----------------------------------------
+// Row ownership of the m x q panels during the MM loop: sharded() -> every GPU computes the rows of S it owns (and the tail
+// kernels exchange q x q partials / statistics through the mailboxes and store finished operand rows into every peer);
+// otherwise (data-matrix mode, or no peer access) every GPU runs the tail redundantly on all m rows with no exchange.
+int Solver::op_tail(const TailSpec& ts, const PanelDims& pd, const StageConsts& sc) {
+  const bool sh = sharded();
+  const int nr = sh ? prob.world : 1;
+  const int wpar = ts.site >= 0 ? warm_parity[ts.site] : 0;
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    TailArgs a;
+    a.row0 = sh ? d.lo : 0;
+    a.row1 = sh ? d.hi : m;
+    a.q = pd.q; a.cplx = pd.cplx; a.ncr = pd.ncr; a.pitch = pd.pitch;
+    a.nranks = nr;
+    a.my_rank = sh ? d.shard : 0;
+    a.producer = ts.producer;
+    a.in0 = ts.in0 >= 0 ? d.buf[ts.in0] : nullptr;
+    a.in1 = ts.in1 >= 0 ? d.buf[ts.in1] : nullptr;
+    a.in2 = ts.in2 >= 0 ? d.buf[ts.in2] : nullptr;
+    a.T = d.buf[ts.T];
+    a.d = d.dvec; a.rho = d.rho; a.sc = sc;
+    if (ts.use_prev) {
+      a.prev_flags = d.mail->stat_flag;
+      a.prev_epoch = stat_epoch;
+      a.prev_stat = &d.mail->stat[stat_epoch & 1ull][0][0];
+    }
+    a.a_cur = d.a_cur;
+    a.retry = ts.retry;
+    const bool all = ts.out_all && sh && nr > 1;
+    for (int r = 0; r < nr; ++r) {
+      char* base = sh ? d.peer_arena[r] : static_cast<char*>(d.arena);
+      a.out_peer[r] = reinterpret_cast<double*>(base + d.off_buf[ts.out]);
+      a.mail[r] = reinterpret_cast<Mailbox*>(base + d.off_mail);
+    }
+    a.n_out = all ? nr : 1;
+    a.skip_polar = ts.skip_polar ? 1 : 0;
+    a.want_absmin = ts.absmin; a.want_gsum = ts.gsum; a.want_squarem = ts.squarem;
+    a.sq_V = ts.sqV >= 0 ? d.buf[ts.sqV] : nullptr;
+    a.sq_V1 = ts.sqV1 >= 0 ? d.buf[ts.sqV1] : nullptr;
+    a.gram_epoch = d.gram_epoch;
+    a.stat_epoch = stat_epoch + 1;
+    a.cta_part = d.cta_part; a.cta_stat = d.cta_stat; a.ticket = d.tail_ticket;
+    if (ts.site >= 0) {
+      double* wbase = d.twarm + static_cast<size_t>(ts.site) * 2 * kWarmDoubles;
+      a.warm_in = wbase + static_cast<size_t>(wpar) * kWarmDoubles;
+      a.warm_out = wbase + static_cast<size_t>(wpar ^ 1) * kWarmDoubles;
+    }
+    a.status = d.tstatus;
+    a.diag = d.tdiag;
+    a.spin_budget_ns = static_cast<long long>(cfg.exchange_timeout_ms > 0 ? cfg.exchange_timeout_ms : 10000) * 1000000ll;
+    SPE_TRY(launch_tail(a, d.num_sms, d.st));
+  }
+  ++stat_epoch;
+  if (!ts.skip_polar && ts.site >= 0) warm_parity[ts.site] ^= 1;
+  return SPEIGEN_OK;
+}
+
+int Solver::op_contract_loop(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vepi, bool want_dots, const StageConsts& sc) {
+  if (!sharded()) {
+    // replicated tails: the contraction gathers full panels as before; the column minima come from the own mailbox
+    for (Dev& d : devs) d.wmax = &d.mail->stat[stat_epoch & 1ull][0][kStatAbsmin];
+    return op_contract(in, pd, outY, outB, vepi, want_dots, sc);
+  }
+  const bool multi = prob.world > 1;
+  const bool want_y = outY != NBUF, want_b = outB != NBUF;
+  const int parity = static_cast<int>(epoch & 1);
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    const double* operand = d.buf[in];
+    const long long budget = static_cast<long long>(cfg.exchange_timeout_ms > 0 ? cfg.exchange_timeout_ms : 10000) * 1000000ll;
+    if (cplx) {
+      // the complex operand expansion reads the whole panel: wait for the peers' rows first (tiny kernel on the same stream)
+      if (multi) SPE_TRY(launch_wait_flags(d.mail->stat_flag, kFlagStride, prob.world, stat_epoch, d.tstatus, budget, d.st));
+      SPE_TRY(launch_hat(pd, d.buf[in], d.hat, /*conj_form=*/1, d.st));
+      operand = d.hat;
+    }
+    EpiArgs ep;
+    ep.q = pd.q; ep.cplx = cplx; ep.pitch = pd.pitch; ep.sc = sc;
+    ep.row_off = d.lo;
+    ep.Y = want_y ? d.buf[outY] : nullptr;
+    if (want_b) { ep.B = d.buf[outB]; ep.d = d.dvec; ep.rho = d.rho; }
+    if (want_b || want_dots) ep.V = d.buf[vepi];
+    if (want_dots) ep.dots = d.dots_part;
+    ep.wait_flags = d.mail->stat_flag;
+    ep.wait_n = prob.world;
+    ep.wait_epoch = stat_epoch;
+    ep.stat_absmin = &d.mail->stat[stat_epoch & 1ull][0][kStatAbsmin];
+    ep.stat_n = prob.world;
+    ep.stat_stride = kStatLen;
+    ep.status = d.tstatus;
+    ep.spin_budget_ns = budget;
+    if (multi && want_dots) {
+      ep.npeers = prob.world;
+      ep.my_shard = d.shard;
+      for (int r = 0; r < prob.world; ++r) {
+        ep.peer_dots[r] = d.peer_xdots[r] + static_cast<size_t>(parity) * prob.world * kMaxCols;
+        ep.peer_flag[r] = d.peer_xflags[r];
+      }
+      ep.epoch = epoch + 1;
+      ep.done_count = d.done_count;
+    }
+    const bool tme = ktiming && (&d == &devs[0]) && kev_used + 2 <= kev.size();
+    if (tme) SPE_CUDA(cudaEventRecord(kev[kev_used], d.st));
+    SPE_TRY(launch_contract_std(d.Astd, operand, pd.ncr, ep, d.ws, d.num_sms, d.st));
+    if (tme) { SPE_CUDA(cudaEventRecord(kev[kev_used + 1], d.st)); kev_used += 2; }
+  }
+  contractions++;
+  if (multi && want_dots) { ++epoch; dots_parity = parity; }
+  n_dot_parts = multi ? prob.world : static_cast<int>((devs[0].a_rows + kTJ - 1) / kTJ);
+  return SPEIGEN_OK;
+}
+
+// F = sum_c d_c quad_c - sum_c rho_c gsum_c (R/spEigen.R:136-138) from the last contraction's dot partials and the last
+// tail's penalty sums; lands in h_res (mapped pinned memory) - the caller synchronises device 0's stream and reads it.
+int Solver::op_finish_objective(const PanelDims& pd) {
+  const bool sh = sharded();
+  const bool multi_sh = sh && prob.world > 1;
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    FinishArgs f;
+    f.q = pd.q;
+    f.nranks = sh ? prob.world : 1;
+    if (multi_sh) {
+      f.dots = d.xdots + static_cast<size_t>(dots_parity) * prob.world * kMaxCols;
+      f.n_dot_parts = prob.world;
+      f.dots_flags = d.xflags;
+      f.dots_epoch = epoch;
+    } else {
+      f.dots = d.dots_part;
+      f.n_dot_parts = n_dot_parts;
+    }
+    f.stat_flags = d.mail->stat_flag;
+    f.stat_epoch = stat_epoch;
+    f.stat = &d.mail->stat[stat_epoch & 1ull][0][0];
+    f.d = d.dvec; f.rho = d.rho;
+    f.diag = d.tdiag;
+    f.status = d.tstatus;
+    f.out = d.scal + 8;
+    f.out_host = (&d == &devs[0]) ? d.res_host_dev : nullptr;
+    f.spin_budget_ns = static_cast<long long>(cfg.exchange_timeout_ms > 0 ? cfg.exchange_timeout_ms : 10000) * 1000000ll;
+    SPE_TRY(launch_finish_objective(f, d.st));
+  }
+  return SPEIGEN_OK;
+}
+
+int Solver::check_tail_status(double sv) {
+  const int st = static_cast<int>(sv);
+  if (st == 0) return SPEIGEN_OK;
+  for (Dev& d : devs) {          // the flag is sticky on the device: clear it so that the solver stays usable
+    cudaSetDevice(d.ordinal);
+    cudaMemsetAsync(d.tstatus, 0, sizeof(int), d.st);
+  }
+  if (st & 4) {
+    set_error("a GPU waited more than %d ms for a peer in the fused exchange (a rank failed or left early)", cfg.exchange_timeout_ms);
+    return SPEIGEN_ERR_TIMEOUT;
+  }
+  set_error("a Procrustes target (G - H of R/spEigen.R:180) is %s: its polar factor is not defined",
+            (st & 1) ? "non-finite or zero" : "rank deficient beyond double precision");
+  return SPEIGEN_ERR_NUMERIC;
 }
 
 // ---- initialiser: block subspace iteration with Rayleigh-Ritz (replaces eigen()/svd()) ----------
@@ -856,12 +1069,20 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
 }
 
 // ---- the MM loop (R/spEigen.R:105-160) ----------------------------------------------------------
+// Per outer iteration k (5 launches + 3 per backtrack, one host read-back per try):
+//   tail   V1 = polar(reweight(S V, V))                         -> rows of V1 on every GPU, min|V1|
+//   K1     B  = reweight(S V1, V1)   (fused epilogue, own rows)
+//   tail   V2 = polar(B)                                        -> ||R||^2, ||U||^2
+//   tail   V0 = polar(V - 2aR + a^2 U), a on the device         -> rows of V0 on every GPU, min|V0|, penalty sums
+//   K1     Y0 = S V0 (own rows) + column dots Re(V0^H Y0)
+//   finish F  -> mapped pinned memory
 int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) {
   if (!inited) { set_error("solver_run before solver_init"); return SPEIGEN_ERR_ARG; }
   const double t0 = now_s();
   for (Dev& d : devs) {
     SPE_CUDA(cudaSetDevice(d.ordinal));
-    SPE_CUDA(cudaMemsetAsync(d.warm, 0, 4 * kWarmStride * sizeof(double), d.st));
+    SPE_CUDA(cudaMemsetAsync(d.twarm, 0, static_cast<size_t>(N_TAIL_SITES) * 2 * kWarmDoubles * sizeof(double), d.st));
+    SPE_CUDA(cudaMemsetAsync(d.tstatus, 0, sizeof(int), d.st));
   }
   std::vector<double> dv(q), rv(q);
   if (d_in) for (int c = 0; c < q; ++c) dv[c] = d_in[c];
@@ -873,85 +1094,70 @@ int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) 
   const int K = cfg.n_continuation;
   std::vector<double> pp(K + 1), ee(K + 1), tl(K + 1);
   speigen_schedule(&cfg, pp.data(), ee.data(), tl.data());
-  const bool fused = cfg.fused_epilogue != 0;
+  const bool fused = cfg.fused_epilogue != 0 && !(data && prob.world > 1);
   const int64_t c_before = contractions;
 
   StageConsts sc = make_stage(pp[0], ee[0]);
-  // Y = S V for the start point; min|V| partials for the weights' column max
-  SPE_TRY(op_contract(BV, pdq, BY, NBUF, NBUF, false, sc));
-  for (Dev& d : devs) {
-    SPE_CUDA(cudaSetDevice(d.ordinal));
-    SPE_TRY(launch_absmin(pdq, d.buf[BV], d.absmin_a, d.ps.ticket, d.st));
-  }
   Buf bV = BV, bV0 = BV0, bY = BY, bY0 = BY0;
-  bool absmin_swapped = false;   // false: accepted iterate's partials live in absmin_a
+  // start point: its column minima (and, row-sharded, nothing else to distribute: V is replicated by the initialiser)
+  {
+    TailSpec ts;
+    ts.T = bV; ts.out = bV; ts.skip_polar = true; ts.absmin = true;
+    SPE_TRY(op_tail(ts, pdq, sc));
+  }
+  SPE_TRY(op_contract_loop(bV, pdq, bY, NBUF, NBUF, false, sc));      // Y = S V
   std::vector<double> Fv;
   int k = 0, total_bt = 0;
-  bool hit_max = false;
-  for (int st = 0; st <= K && !hit_max; ++st) {
+  const int o_diag = 1 + 2 * q;
+  for (int st = 0; st <= K; ++st) {
     sc = make_stage(pp[st], ee[st]);
     int flg = 1;
     while (true) {
       ++k;
-      // ---- V1 = MMupdate(V) ----
-      for (Dev& d : devs) {
-        SPE_CUDA(cudaSetDevice(d.ordinal));
-        d.wmax = const_cast<double*>(absmin_final(absmin_swapped ? d.absmin_b : d.absmin_a));   // min|V| -> weights' column max
-        SPE_TRY(launch_reweight(pdq, d.buf[bY], d.buf[bV], d.dvec, d.rho, d.wmax, sc, d.buf[BB], d.ps.gram_part, d.st));
+      // ---- V1 = MMupdate(V): reweighting from the inherited Y = S V, then the polar factor ----
+      {
+        TailSpec ts;
+        ts.producer = TAIL_REWEIGHT; ts.in0 = bY; ts.in1 = bV; ts.T = BB; ts.out = BV1; ts.out_all = true;
+        ts.absmin = true; ts.use_prev = true; ts.site = SITE_MM1;
+        SPE_TRY(op_tail(ts, pdq, sc));
       }
-      const int other = absmin_swapped ? 1 : 2;   // scratch min|.| partial buffer (1 = a, 2 = b)
-      SPE_TRY(op_polar(BB, BV1, pdq, true, nullptr, other, WARM_MM));
       // ---- V2 = MMupdate(V1): contraction with the reweighting fused into its epilogue ----
-      for (Dev& d : devs) {
-        SPE_CUDA(cudaSetDevice(d.ordinal));
-        d.wmax = const_cast<double*>(absmin_final(other == 1 ? d.absmin_a : d.absmin_b));
-      }
       if (fused) {
-        SPE_TRY(op_contract(BV1, pdq, NBUF, BB, BV1, false, sc));
-        SPE_TRY(op_polar(BB, BV2, pdq, false, nullptr, 0, WARM_MM));
+        SPE_TRY(op_contract_loop(BV1, pdq, NBUF, BB, BV1, false, sc));
+        TailSpec ts;
+        ts.producer = TAIL_PANEL; ts.T = BB; ts.out = BV2; ts.squarem = true; ts.sqV = bV; ts.sqV1 = BV1; ts.site = SITE_MM2;
+        SPE_TRY(op_tail(ts, pdq, sc));
       } else {
-        SPE_TRY(op_contract(BV1, pdq, BT1, NBUF, NBUF, false, sc));
-        for (Dev& d : devs) {
-          SPE_CUDA(cudaSetDevice(d.ordinal));
-          SPE_TRY(launch_reweight(pdq, d.buf[BT1], d.buf[BV1], d.dvec, d.rho, d.wmax, sc, d.buf[BB], d.ps.gram_part, d.st));
-        }
-        SPE_TRY(op_polar(BB, BV2, pdq, true, nullptr, 0, WARM_MM));
+        SPE_TRY(op_contract_loop(BV1, pdq, BT1, NBUF, NBUF, false, sc));
+        TailSpec ts;
+        ts.producer = TAIL_REWEIGHT; ts.in0 = BT1; ts.in1 = BV1; ts.T = BB; ts.out = BV2; ts.use_prev = true;
+        ts.squarem = true; ts.sqV = bV; ts.sqV1 = BV1; ts.site = SITE_MM2;
+        SPE_TRY(op_tail(ts, pdq, sc));
       }
-      // ---- SQUAREM step length  (R/spEigen.R:121-123) ----
-      for (Dev& d : devs) {
-        SPE_CUDA(cudaSetDevice(d.ordinal));
-        SPE_TRY(launch_squarem_norms(pdq, d.buf[bV], d.buf[BV1], d.buf[BV2], d.ps, d.scal, d.st));
-      }
-      SPE_TRY(read_scalars(2));
-      const double nR = h_scal[0], nU = h_scal[1];
-      // a <- min(-||R||/||U||, -1)   :123.  ||U|| == 0 (V2 - 2 V1 + V vanished exactly) gives -Inf in R and then a NaN
-      // iterate that makes svd() fail; here that case takes the plain double MM step a = -1 (V0 = V2) instead.
-      double a = (nU > 0.0) ? std::min(-nR / nU, -1.0) : -1.0;
-      if (a != a) a = -1.0;
       int nbt = 0;
-      double Fk = 0.0;
+      double Fk = 0.0, a = -1.0, nR = 0.0, nU = 0.0;
       while (true) {                            // backtracking loop, R/spEigen.R:126-146
-        for (Dev& d : devs) {
-          SPE_CUDA(cudaSetDevice(d.ordinal));
-          SPE_TRY(launch_extrapolate(pdq, d.buf[bV], d.buf[BV1], d.buf[BV2], a, d.buf[BT1], d.ps.gram_part, d.st));
-        }
-        SPE_TRY(op_polar(BT1, bV0, pdq, true, nullptr, other, WARM_EXTRAP));
-        SPE_TRY(op_contract(bV0, pdq, bY0, NBUF, bV0, true, sc));
-        for (Dev& d : devs) {
-          SPE_CUDA(cudaSetDevice(d.ordinal));
-          SPE_TRY(launch_objective(pdq, d.buf[bV0], sc, d.dots_part, n_dot_parts, d.dvec, d.rho, d.ps, d.scal + 8, d.st));
-        }
-        SPE_TRY(read_scalars(9));
-        Fk = h_scal[8];
+        // SQUAREM step length a = min(-||R||/||U||, -1) (:121-123) is formed on the device from the statistics of the V2 tail
+        // (first try) or halved from the previous try (:141); extrapolation + projection :127-131
+        TailSpec ts;
+        ts.producer = TAIL_EXTRAP; ts.in0 = bV; ts.in1 = BV1; ts.in2 = BV2; ts.T = BT1; ts.out = bV0; ts.out_all = true;
+        ts.absmin = true; ts.gsum = true; ts.use_prev = (nbt == 0); ts.retry = (nbt > 0) ? 1 : 0; ts.site = SITE_EXTRAP;
+        SPE_TRY(op_tail(ts, pdq, sc));
+        SPE_TRY(op_contract_loop(bV0, pdq, bY0, NBUF, bV0, true, sc));
+        SPE_TRY(op_finish_objective(pdq));
+        SPE_CUDA(cudaSetDevice(devs[0].ordinal));
+        SPE_CUDA(cudaStreamSynchronize(devs[0].st));
+        SPE_TRY(check_tail_status(h_res[o_diag + 5]));
+        Fk = h_res[0];
+        a = h_res[o_diag + 0];
+        if (nbt == 0) { nR = h_res[o_diag + 1]; nU = h_res[o_diag + 2]; }
         const double Fprev = Fv.empty() ? Fk : Fv[std::max(k - 1, 1) - 1];
         const double sgn = (Fk > 0) - (Fk < 0);
         if (flg == 0 && Fk * (1.0 + sgn * cfg.backtrack_slack) <= Fprev && nbt < cfg.max_backtracks) {
-          a = (a - 1.0) / 2.0;                  // :141
-          ++nbt;
+          ++nbt;                                // a <- (a - 1) / 2   :141 (on the device, next try)
         } else {
           std::swap(bV, bV0);                   // V <- V0   :143
           std::swap(bY, bY0);
-          absmin_swapped = !absmin_swapped;
           break;
         }
       }
@@ -964,17 +1170,19 @@ int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) 
         if (out->stage_of_k) out->stage_of_k[k - 1] = st + 1;
       }
       if (cfg.verbose) fprintf(stderr, "[speigen] stage %d k %d: nR=%.3e nU=%.3e a=%.4g bt=%d F=%.15g\n", st + 1, k, nR, nU, a, nbt, Fk);
-      if (flg == 0) {                           // stopping criterion  :149-153
+      if (flg == 0) {                           // stopping criterion  :149-153 (k >= max_iter ends this stage only, as in R)
         const double Fp = Fv[k - 2];
         const double rel = std::fabs(Fk - Fp) / std::max(1.0, std::fabs(Fp));
-        if (rel <= tl[st]) break;
-        if (k >= cfg.max_iter) { hit_max = true; break; }
+        if (rel <= tl[st] || k >= cfg.max_iter) break;
       }
       flg = 0;
     }
   }
   // threshold + normalise + outputs   :158-162
   if (out) {
+    // every rank holds every row of the accepted iterate (the extrapolation tail stores its rows to all ranks); make sure the
+    // peers' stores have landed before device 0 reads the panel
+    SPE_TRY(wait_latest_tail());
     Dev& d = devs[0];
     SPE_CUDA(cudaSetDevice(d.ordinal));
     const size_t bytes = static_cast<size_t>(m) * pdq.ncr * sizeof(double);
@@ -991,15 +1199,25 @@ int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) 
     out->contractions = static_cast<int>(contractions - c_before);
     out->seconds_loop = now_s() - t0;
   }
-  {
-    Dev& d = devs[0];
-    int stt = 0;
-    SPE_CUDA(cudaSetDevice(d.ordinal));
-    SPE_CUDA(cudaMemcpyAsync(&stt, d.status, sizeof(int), cudaMemcpyDeviceToHost, d.st));
-    SPE_CUDA(cudaStreamSynchronize(d.st));
-    if (stt && cfg.verbose) fprintf(stderr, "[speigen] warning: a rank-deficient Gram matrix was met in a polar step\n");
-  }
   SPE_TRY(sync_all());
+  {
+    int stt = 0;
+    Dev& d = devs[0];
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_CUDA(cudaMemcpy(&stt, d.tstatus, sizeof(int), cudaMemcpyDeviceToHost));
+    SPE_TRY(check_tail_status(static_cast<double>(stt)));
+  }
+  return SPEIGEN_OK;
+}
+
+// all ranks' rows of the latest tail's output panel have arrived on every local device (host-side wait on the stat flags)
+int Solver::wait_latest_tail() {
+  if (!sharded() || prob.world == 1) return SPEIGEN_OK;
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_TRY(launch_wait_flags(d.mail->stat_flag, kFlagStride, prob.world, stat_epoch, d.tstatus,
+                              static_cast<long long>(cfg.exchange_timeout_ms > 0 ? cfg.exchange_timeout_ms : 10000) * 1000000ll, d.st));
+  }
   return SPEIGEN_OK;
 }
 
@@ -1062,9 +1280,12 @@ int Solver::mm_steps(int nsteps, int stage, double rho, const double* d_in, floa
   speigen_schedule(&cfg, pp.data(), ee.data(), tl.data());
   if (stage < 0 || stage > K) stage = 0;
   const StageConsts sc = make_stage(pp[stage], ee[stage]);
-  for (Dev& d : devs) {
-    SPE_CUDA(cudaSetDevice(d.ordinal));
-    SPE_TRY(launch_absmin(pdq, d.buf[BV], d.absmin_a, d.ps.ticket, d.st));
+  const bool fused = !(data && prob.world > 1);
+  Buf bA = BV, bB = BV1;
+  {
+    TailSpec ts;   // column minima of the resident iterate
+    ts.T = bA; ts.out = bA; ts.skip_polar = true; ts.absmin = true;
+    SPE_TRY(op_tail(ts, pdq, sc));
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ms_out) {
@@ -1075,13 +1296,17 @@ int Solver::mm_steps(int nsteps, int stage, double rho, const double* d_in, floa
     SPE_CUDA(cudaEventRecord(e0, devs[0].st));
   }
   for (int i = 0; i < nsteps; ++i) {
-    for (Dev& d : devs) {
-      SPE_CUDA(cudaSetDevice(d.ordinal));
-      d.wmax = const_cast<double*>(absmin_final(d.absmin_a));
+    TailSpec ts;
+    ts.out = bB; ts.out_all = true; ts.absmin = true; ts.site = SITE_MM1; ts.T = BB;
+    if (fused) {
+      SPE_TRY(op_contract_loop(bA, pdq, NBUF, BB, bA, false, sc));     // K1 with the fused reweighting epilogue
+      ts.producer = TAIL_PANEL;
+    } else {
+      SPE_TRY(op_contract_loop(bA, pdq, BT1, NBUF, NBUF, false, sc));
+      ts.producer = TAIL_REWEIGHT; ts.in0 = BT1; ts.in1 = bA; ts.use_prev = true;
     }
-    SPE_TRY(op_contract(BV, pdq, NBUF, BB, BV, false, sc));     // K1 with the fused reweighting epilogue
-    SPE_TRY(op_polar(BB, BV1, pdq, false, nullptr, 1, WARM_MM)); // K3 (+ min|V| partials for the next weights)
-    for (Dev& d : devs) std::swap(d.buf[BV], d.buf[BV1]);
+    SPE_TRY(op_tail(ts, pdq, sc));                                     // fused polar tail (+ min|V| for the next weights)
+    std::swap(bA, bB);
   }
   if (ms_out) {
     SPE_CUDA(cudaSetDevice(devs[0].ordinal));
@@ -1090,6 +1315,21 @@ int Solver::mm_steps(int nsteps, int stage, double rho, const double* d_in, floa
     SPE_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+  }
+  if (bA != BV) {        // leave the final iterate in BV (all rows are present on every rank once the peers' flags are up)
+    SPE_TRY(wait_latest_tail());
+    for (Dev& d : devs) {
+      SPE_CUDA(cudaSetDevice(d.ordinal));
+      SPE_CUDA(cudaMemcpyAsync(d.buf[BV], d.buf[bA], static_cast<size_t>(mrows) * pdq.pitch * sizeof(double), cudaMemcpyDeviceToDevice, d.st));
+    }
+  }
+  SPE_TRY(sync_all());
+  {
+    int stt = 0;
+    Dev& d = devs[0];
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    SPE_CUDA(cudaMemcpy(&stt, d.tstatus, sizeof(int), cudaMemcpyDeviceToHost));
+    SPE_TRY(check_tail_status(static_cast<double>(stt)));
   }
   return SPEIGEN_OK;
 }

@@ -9,12 +9,29 @@
 #include "contract.cuh"
 #include "panel_ops.cuh"
 #include "matrix_ops.cuh"
+#include "tail.cuh"
 #include "nccl_shim.h"
 
 namespace speigen {
 
 constexpr size_t kWarmStride = 2 + 2 * kMaxCols * kMaxCols;
 enum WarmSlot { WARM_MM = 0, WARM_EXTRAP = 1, WARM_INIT = 2 };
+enum TailSite { SITE_MM1 = 0, SITE_MM2 = 1, SITE_EXTRAP = 2, SITE_MISC = 3, N_TAIL_SITES = 4 };
+
+// One call of the fused polar tail (tail.cuh) in terms of the solver's panel buffers.
+struct TailSpec {
+  int producer = TAIL_PANEL;
+  int in0 = -1, in1 = -1, in2 = -1;   // Buf indices (producer inputs)
+  int T = -1;                         // work panel
+  int out = -1;                       // destination panel
+  bool out_all = false;               // row-sharded: store the finished rows into every rank's copy (next contraction operand)
+  bool skip_polar = false;
+  bool absmin = false, gsum = false, squarem = false;
+  int sqV = -1, sqV1 = -1;
+  bool use_prev = false;              // consume the previous tail's statistics (absmin / squarem sums)
+  int retry = 0;
+  int site = -1;                      // Jacobi warm-start slot (TailSite); -1: cold start, history-free
+};
 enum Buf { BV = 0, BV1, BV2, BV0, BY, BY0, BB, BT1, BT2, BVX, BQ, BZ, NBUF };
 
 struct Dev {
@@ -63,8 +80,24 @@ struct Dev {
   double* peer_xb[kMaxPeers] = {};         // the same buffers of every shard as mapped into this device
   double* peer_xdots[kMaxPeers] = {};
   unsigned long long* peer_xflags[kMaxPeers] = {};
-  void* ipc_opened[3 * kMaxPeers] = {};
+  void* ipc_opened[5 * kMaxPeers] = {};
   int n_ipc_opened = 0;
+  // ---- round 2: fused row-sharded tail (tail.cuh).  The panels and the mailbox sit at the head of the arena at offsets that
+  // are identical on every rank, so a peer's copy of any panel is peer_arena[r] + off_buf[b].
+  char* peer_arena[kMaxPeers] = {};
+  const double* peer_A[kMaxPeers] = {};    // the peers' matrix shards (symmetry scan across processes)
+  size_t off_buf[NBUF] = {};
+  size_t off_mail = 0;
+  Mailbox* mail = nullptr;
+  double* cta_part = nullptr;              // [num_sms][kTriMax]
+  double* cta_stat = nullptr;              // [num_sms][kStatLen]
+  int* tail_ticket = nullptr;              // [2]
+  unsigned long long* gram_epoch = nullptr;
+  double* a_cur = nullptr;
+  double* tdiag = nullptr;                 // [8]
+  int* tstatus = nullptr;
+  double* twarm = nullptr;                 // [N_TAIL_SITES][2][kWarmDoubles]
+  double* res_host_dev = nullptr;          // device view of the solver's mapped result block (device 0 only)
 };
 
 class Solver {
@@ -119,8 +152,21 @@ class Solver {
   int kernel_time(double* ms_total, int* launches);
   int exchange_allgather(Buf b, const PanelDims& pd);
   int init_p2p();
-  bool p2p = false;
+  bool p2p = false;       // fused peer-store exchange in use
+  bool peer_ok = false;   // every shard's buffers are mapped into every local device (peer access / CUDA IPC)
   unsigned long long epoch = 0;   // contraction counter of the fused exchange (identical on every rank)
+  // ---- round 2: row-sharded MM loop
+  bool sharded() const { return !data && (prob.world == 1 || p2p); }   // tails run on the own rows only
+  unsigned long long stat_epoch = 0;          // tail calls so far (identical on every rank)
+  int warm_parity[N_TAIL_SITES] = {};
+  double* h_res = nullptr;                    // mapped pinned result block written by k_finish_objective
+  int op_tail(const TailSpec& ts, const PanelDims& pd, const StageConsts& sc);
+  // K1 of the MM loop: own rows only, operand / column minima taken from the latest tail (waits for its flags)
+  int op_contract_loop(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vepi, bool want_dots, const StageConsts& sc);
+  int op_finish_objective(const PanelDims& pd);
+  int check_tail_status(double status_value);
+  int wait_latest_tail();
+  int dots_parity = 0;
 
  private:
   int alloc_dev(Dev& d);

@@ -56,8 +56,13 @@ def test_e2e_two_gpus_matches_one():
     S = o.sample_cov(X)
     a = sb.spEigen(S, 5, n_gpus=1)
     b = sb.spEigen(S, 5, n_gpus=2)
-    b0 = sb.spEigen(S, 5, n_gpus=2, p2p_exchange=0)
-    assert np.array_equal(b["vectors"], b0["vectors"]) and np.array_equal(b["info"]["F"], b0["info"]["F"])
+    b0 = sb.spEigen(S, 5, n_gpus=2, p2p_exchange=0)        # NCCL allgather of row blocks, tails replicated on all rows
+    # the row-sharded tails sum their Gram partials per rank, the replicated ones over all rows at once: same result up to
+    # the summation order
+    nb = min(len(b["info"]["F"]), len(b0["info"]["F"]), 10)
+    assert np.allclose(b["info"]["F"][:nb], b0["info"]["F"][:nb], rtol=1e-11)
+    assert np.array_equal(b["vectors"] != 0, b0["vectors"] != 0)
+    assert np.all(colwise_inner(b["vectors"], b0["vectors"]) > 1 - 1e-8)
     n = min(len(a["info"]["F"]), len(b["info"]["F"]), 10)
     assert np.allclose(a["info"]["F"][:n], b["info"]["F"][:n], rtol=1e-11)
     assert np.array_equal(a["vectors"] != 0, b["vectors"] != 0)
