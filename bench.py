@@ -1,27 +1,35 @@
 #!/usr/bin/env python
 """bench.py — spEigen MM iterations/s and contraction-kernel roofline on B200.
 
-Workload (BASELINE.json metric): spEigen covariance input m=50000, q=20, real FP64 (S = 20 GB),
-row-sharded over N GPUs with an NCCL allgather of the m x q block per contraction.
-A step = ONE MM update  V <- spEigenMMupdate(V)  (R/spEigen.R:167-183): one streamed contraction over S
-with the reweighting fused in its epilogue + the polar (Procrustes) update.
+Workload (BASELINE.json metric): spEigen covariance input m=50000, q=20, real FP64 (S = 20 GB), row-sharded over N GPUs.
+A step = ONE MM update  V <- spEigenMMupdate(V)  (R/spEigen.R:167-183): one streamed contraction over S with the
+reweighting fused in its epilogue (K1) + the fused polar tail kernel (Gram passes, q x q Jacobi/Taylor solve, applies,
+column minima; row-sharded across the GPUs with peer-memory exchanges).
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
-  python bench.py --impl reference ...                     (CPU arm: the oracle port, NumPy/OpenBLAS)
+  python bench.py --impl reference ...                     (CPU arm: the oracle port, NumPy/OpenBLAS on all host cores)
 
 torch is used for plumbing only: device RNG/GEMM to synthesise S, torch.distributed for the bootstrap.
 """
 from __future__ import annotations
 
-import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU legs of this script (reference arm, cpu_baseline) are
+# meant to use every host core.  The BLAS thread pools read these variables when NumPy loads, so fix them first.
+_HOST_CORES = os.cpu_count() or 1
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = str(_HOST_CORES)
+
+import argparse          # noqa: E402
+import hashlib           # noqa: E402
+import json              # noqa: E402
+import subprocess        # noqa: E402
+import threading         # noqa: E402
+import time              # noqa: E402
+
+import numpy as np       # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -34,8 +42,10 @@ os.dup2(2, 1)
 def emit(line):
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
+
 METRIC = "spEigen MM iters/sec (m=50k cov, q=20)"
 UNIT = "MM iters/s"
+DMMA_PEAK_TF = 37.0      # FP64 tensor pipe measured on this pool (profiles/r01_microbench_fp64_pipes.log)
 
 
 def peaks():
@@ -44,6 +54,18 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def blas_threads():
+    """Threads the BLAS behind NumPy will really use (threadpoolctl), next to the core count."""
+    try:
+        from threadpoolctl import threadpool_info
+        info = [i for i in threadpool_info() if i.get("user_api") == "blas"]
+        if info:
+            return int(max(i["num_threads"] for i in info)), str(info[0].get("internal_api", "blas")) + " " + str(info[0].get("version", ""))
+    except Exception:
+        pass
+    return _HOST_CORES, "OpenBLAS (numpy)"
 
 
 class ClockSampler:
@@ -90,21 +112,24 @@ class ClockSampler:
 
 def ncu_traffic_bytes(m, q, world):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the contraction kernel from the committed ncu --set full
-    capture (profiles/r01_ncu_prof_contract_r01.csv), valid for the default single-GPU workload only; else None."""
+    capture (profiles/r0?_ncu_prof_contract*.csv), valid for the default single-GPU workload only; else None."""
     if (m, q, world) != (50000, 20, 1):
-        return None
-    p = os.path.join(ROOT, "profiles", "r01_ncu_prof_contract_r01.csv")
-    try:
-        rd = wr = None
-        for line in open(p):
-            f = line.strip().split(",")
-            if f[0] == "dram__bytes_read.sum":
-                rd = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
-            if f[0] == "dram__bytes_write.sum":
-                wr = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
-        return rd + wr if rd is not None and wr is not None else None
-    except OSError:
-        return None
+        return None, None
+    for name in ("r02_ncu_prof_contract.csv", "r01_ncu_prof_contract_r01.csv"):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            rd = wr = None
+            for line in open(p):
+                f = line.strip().split(",")
+                if f[0] == "dram__bytes_read.sum":
+                    rd = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+                if f[0] == "dram__bytes_write.sum":
+                    wr = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+            if rd is not None and wr is not None:
+                return rd + wr, f"profiles/{name} (ncu --set full, one launch; not measured in this run)"
+        except OSError:
+            continue
+    return None, None
 
 
 def synth_cov_rows(m, n, q, card, lo, hi, device, seed=42):
@@ -132,7 +157,6 @@ def synth_cov_rows(m, n, q, card, lo, hi, device, seed=42):
 
 
 def symmetrize_(S):
-    import torch
     m = S.shape[0]
     step = 8192
     for a in range(0, m, step):
@@ -145,7 +169,19 @@ def symmetrize_(S):
     return S
 
 
-def cpu_mm_update_time(S_host, q, steps, threads):
+def host_cov(m, n, q, card, pinned=False):
+    """The full symmetric S on the host: synthesised on GPU 0 (identical bits to the sharded rows), copied down."""
+    import torch
+    dev = torch.device("cuda", 0)
+    S = symmetrize_(synth_cov_rows(m, n, q, card, 0, m, dev))
+    H = torch.empty((m, m), dtype=torch.float64, pin_memory=pinned)
+    H.copy_(S)
+    del S
+    torch.cuda.empty_cache()
+    return H
+
+
+def cpu_mm_update_time(S_host, q, steps, warmup):
     """Oracle port (direct mode) timed on the host: MM updates/s on the same S."""
     from oracle import speigen_oracle as o
     m = S_host.shape[0]
@@ -156,7 +192,8 @@ def cpu_mm_update_time(S_host, q, steps, threads):
     pp, Eps, _ = o.schedule()
     c1, c2, w0 = o.stage_constants(pp[0], Eps[0])
     prob = o.Problem(X=S_host, data=False, q=q, d=d, rho_vec=rho_vec, Vx=None, sv2=np.ones(q), V=V, nrow=m, mode="direct")
-    V = o.mm_update(prob, V, w0, c1, pp[0], Eps[0])       # warm-up
+    for _ in range(max(warmup, 1)):
+        V = o.mm_update(prob, V, w0, c1, pp[0], Eps[0])
     t0 = time.perf_counter()
     for _ in range(steps):
         V = o.mm_update(prob, V, w0, c1, pp[0], Eps[0])
@@ -189,7 +226,6 @@ def bench_speigencov(args):
     clocks = sampler.stop()
     mp = (m + 127) // 128 * 128
     tf = gemms * 2.0 * mp ** 3 / t_gemm / 1e12
-    peak_tf = 37.0
     line = {"metric": "spEigenCov MM iters/sec (m=%d, n=%d, q=%d)" % (m, n, q), "value": its / dt, "unit": "MM iters/s", "n_gpus": 1,
             "steps": its, "warmup": 1, "ms_per_step": 1e3 * dt / its, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -197,7 +233,7 @@ def bench_speigencov(args):
                        "step": "one MM iteration = 1 GEMM (S_hat V) + m x m polar factor (block Jacobi, 3 sweeps + 3 GEMMs) + eigvalAlgo + objective",
                        "l2": "m x m matrices (33.5 MB each) are L2-resident by design; the call re-uploads S and re-creates its context every time",
                        "timed_region": "whole speigencov_run_f64 calls incl. eigen(S), H2D of S, D2H of vectors/values/cov"},
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": DMMA_PEAK_TF, "unit": "TFLOP/s", "frac": tf / DMMA_PEAK_TF, "traffic": None,
                          "kernel": "k_gemm<1,1> (FP64 DMMA)", "ms_per_launch": 1e3 * t_gemm / gemms,
                          "algorithmic_flops_per_launch": 2.0 * mp ** 3, "launches_timed": gemms,
                          "peak_source": "FP64 tensor pipe measured on this pool (profiles/r01_microbench_fp64_pipes.log: DMMA.8x8x4 37.0 TFLOP/s); "
@@ -215,9 +251,18 @@ def bench_speigencov(args):
         t0 = time.perf_counter()
         ro = oc.spEigenCov(S, q, return_trace=True)
         tc = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": len(ro["trace"].F) / tc, "unit": "MM iters/s", "cores": os.cpu_count() or 1, "kind": "port",
+        line["cpu_baseline"] = {"value": len(ro["trace"].F) / tc, "unit": "MM iters/s", "cores": blas_threads()[0], "kind": "port",
                                 "sample": "one full spEigenCov run of the oracle port (NumPy/OpenBLAS eigh + %d gesdd), %.1f s" % (len(ro["trace"].F), tc)}
     emit(line)
+
+
+def e2e_calls(sb, S_host, q, n_gpus, calls):
+    """`calls` drop-in calls speigen_run_f64(S_host, ...) on n_gpus GPUs of THIS process; returns (seconds per call, last result)."""
+    t0 = time.perf_counter()
+    r = None
+    for _ in range(calls):
+        r = sb.spEigen(S_host.T, q, n_gpus=n_gpus, check_symmetric=1)   # .T of the C-ordered symmetric S = R's column-major view, no copy
+    return (time.perf_counter() - t0) / calls, r
 
 
 def main():
@@ -232,9 +277,10 @@ def main():
     ap.add_argument("--card", type=float, default=0.02)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-qsweep", action="store_true")
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=12)
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-store exchange or NCCL allgather")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory exchange or NCCL allgather")
     ap.add_argument("--workload", default="speigen", choices=["speigen", "speigencov"],
                     help="speigen: the BASELINE metric (default); speigencov: BASELINE configs[4] (secondary line)")
     ap.add_argument("--cov-m", type=int, default=2000)
@@ -245,37 +291,38 @@ def main():
         if int(os.environ.get("RANK", "0")) == 0:
             bench_speigencov(args)
         return
-    if args.warmup < 3 and args.impl == "ours":
+    if args.warmup < 3:
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     m, n, q = args.m, args.n, args.q
-    workload = f"spEigen covariance input m={m}, q={q}, real FP64, spiked model n={n} card={args.card} seed 42"
+    # one config for both arms (the driver compares them key by key)
+    config = {"workload": f"spEigen covariance input m={m}, q={q}, real FP64, spiked model n={n} card={args.card} seed 42",
+              "step": "one MM update V <- spEigenMMupdate(V) (R/spEigen.R:167-183) on the full m x m S",
+              "l2": "inputs larger than L2 (the 20 GB S is streamed every step; no flush needed)"}
 
     import torch
     # ---------------------------------------------------------------- reference arm (CPU) ------------
     if args.impl == "reference":
+        # Rank 0 alone runs it (the other ranks exit 0 without work).  R is not installed in this image and the reference is
+        # pure R, so this arm times the oracle port: the NumPy restatement of spEigenMMupdate in direct-S mode (one dgemm + one
+        # thin SVD per update) on every host core.  That is FLATTERING to the CPU: the R code does two dgemm through the full
+        # eigenbasis Vx after an O(m^3) eigen() that cannot run at m = 50k on this host.
         if rank != 0:
             return
-        threads = os.cpu_count() or 1
         dev = "cuda:0" if torch.cuda.is_available() else "cpu"
         S = synth_cov_rows(m, n, q, args.card, 0, m, dev)
         S_host = S.cpu().numpy()
         del S
-        steps = max(1, min(args.steps, 16))
-        for _ in range(min(args.warmup, 1)):
-            cpu_mm_update_time(S_host, q, 1, threads)
-        t0 = time.perf_counter()
-        v = cpu_mm_update_time(S_host, q, steps, threads)
-        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-                "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "note": "R is not installed in this image: the reference arm is the oracle port "
-                           "(NumPy restatement of spEigenMMupdate, direct-S mode = 1 dgemm + svd per update; the R code does 2 dgemm "
-                           "through Vx after an O(m^3) eigen() that cannot run at m=50k)", "blas": "OpenBLAS (numpy)"},
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                 "sample": f"{steps} MM updates on the full {m}x{m} S"},
+        threads, blas = blas_threads()
+        v = cpu_mm_update_time(S_host, q, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "blas": blas, "host_cores": _HOST_CORES,
+                                 "sample": f"{args.steps} MM updates (after {args.warmup} warm-up) of the oracle port on the full {m}x{m} S; "
+                                           f"value does not depend on --gpus"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -288,15 +335,18 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    cpu_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group(backend="nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")      # host-side barriers: a waiting rank must not park a kernel on its GPU
     lo, hi = sb.shard_range(m, world, rank)
     S = synth_cov_rows(m, n, q, args.card, lo, hi, dev)
     if world == 1:
         symmetrize_(S)
+    # isSymmetric.matrix (R/spEigen.R:75) runs in every mode: on one GPU locally, across ranks through the IPC-mapped shards
     solver = sb.Solver(m, q, world=world, rank=rank, local_gpus=1, first_device=local_rank,
-                       check_symmetric=1 if world == 1 else 0, p2p_exchange=1 if args.exchange == "p2p" else 0)
+                       check_symmetric=1, p2p_exchange=1 if args.exchange == "p2p" else 0)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -307,12 +357,6 @@ def main():
         solver.init_comm(None)
     torch.cuda.synchronize()                  # S was produced on torch's stream; the library copies on its own
     solver.load_device(S.data_ptr(), m)
-    S_host = None
-    want_host = (rank == 0 and world == 1 and (not args.no_e2e or not args.no_cpu))
-    if want_host:
-        S_host_t = torch.empty((m, m), dtype=torch.float64, pin_memory=True)
-        S_host_t.copy_(S)
-        S_host = S_host_t.numpy()
     del S
     torch.cuda.empty_cache()
     solver.prepare()
@@ -340,6 +384,7 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = solver.launch_count() - l0
+    tail = solver.tail_diag()
     # max over ranks (device-side work is bracketed by stream syncs; kernel times are CUDA events)
     tt = torch.tensor([wall_ms, k_ms / max(k_n, 1)], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -351,6 +396,22 @@ def main():
     rows_local = hi - lo
     alg_bytes = 8.0 * rows_local * m + 2 * 8.0 * m * q   # 8 m^2 / P + 16 m q per GPU
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    ncols_dmma = (q + 7) // 8 * 8
+    flops_padded = 2.0 * rows_local * m * ncols_dmma
+
+    # K1 alone for q in {8, 16, 20} (single GPU): the HBM-bound regime (q <= 16) next to the FP64-pipe-bound one (q = 20 -> 24)
+    q_sweep = None
+    if world == 1 and not args.no_qsweep:
+        q_sweep = []
+        for qq in (8, 16, 20):
+            if qq > q:
+                continue
+            ms = np.median(solver.time_contract(qq, 12, flush_l2=False)[2:])
+            ab = 8.0 * m * m + 16.0 * m * qq
+            pad = (qq + 7) // 8 * 8
+            q_sweep.append({"q": qq, "ms_per_launch": float(ms), "algorithmic_bytes_per_launch": ab, "achieved_gbs": ab / ms * 1e-6,
+                            "frac_hbm": ab / ms * 1e-6 / peak, "dmma_columns": pad,
+                            "frac_dmma_padded": 2.0 * m * m * pad / (ms * 1e-3) / 1e12 / DMMA_PEAK_TF})
 
     # real full solve on the resident matrix (reports the actual loop: outer iterations, contractions)
     solver.init()
@@ -360,49 +421,95 @@ def main():
     info = res["info"]
     nz = (res["vectors"] != 0).sum(axis=0)
 
+    traffic, traffic_src = ncu_traffic_bytes(m, q, world)
+    config_ours = dict(config)
+    config_ours["sharding"] = f"S row-sharded over {world} GPU(s); per MM update: K1 on the own rows, fused tail kernel on the own rows, " \
+                              f"exchange: {solver.exchange_mode()} (q x q Gram partials + statistics through peer mailboxes, operand rows stored to every peer)"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload, "sharding": f"S row-sharded over {world} GPU(s), exchange per contraction: {solver.exchange_mode()}",
-                       "l2": "inputs larger than L2 (S shard = %.1f GB per GPU streamed every step)" % (8.0 * rows_local * m / 1e9),
-                       "step": "one MM update = fused contraction+reweight, 2x(Gram, Jacobi, apply)"},
+            "data": "synthetic", "config": config_ours,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_bytes(m, q, world), "traffic_source": "profiles/r01_ncu_prof_contract_r01.csv (ncu --set full, one launch)",
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "k_contract_std<3,0>", "ms_per_launch": kern_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "launches_timed": k_n},
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "launches_timed": k_n,
+                         "second_ceiling": {"bound": "fp64 tensor pipe (q=20 padded to %d DMMA columns)" % ncols_dmma,
+                                            "achieved_tflops": flops_padded / (kern_ms * 1e-3) / 1e12, "peak_tflops": DMMA_PEAK_TF,
+                                            "frac": flops_padded / (kern_ms * 1e-3) / 1e12 / DMMA_PEAK_TF},
+                         "q_sweep": q_sweep},
             "gpu_launches": int(launches),
+            "tail_kernel": {"us_per_step_outside_K1": 1e3 * (step_ms - kern_ms), "gram_passes": tail["passes"], "jacobi_sweeps": tail["sweeps"],
+                            "phase_clock_us_cta0": tail["clock_us"]},
             "full_solve": {"seconds_loop": info["seconds_loop"], "seconds_total": solve_s, "outer_iterations": info["iterations"],
                            "backtracks": info["backtracks"], "contractions": info["contractions"],
                            "outer_iters_per_s": info["iterations"] / info["seconds_loop"],
                            "init_passes": init_info["init_passes"], "init_seconds": init_info["seconds_init"],
                            "nonzeros_per_vector": [int(x) for x in nz[:4]], "F_final": float(info["F"][-1])},
             "clocks": clocks}
-    if rank == 0 and world == 1:
-        if not args.no_e2e:
-            # end to end through the drop-in C ABI call with HOST buffers (H2D of S and D2H of results inside)
-            solver.close()
-            torch.cuda.empty_cache()
-            calls = max(1, args.e2e_calls)
-            sb.spEigen(np.asfortranarray(S_host[:2048, :2048]), q)   # warm the context on a small case
-            t_e = time.perf_counter(); upd = 0
-            for _ in range(calls):
-                r = sb.spEigen(S_host.T, q, check_symmetric=1)   # .T of the C-ordered symmetric S = R's column-major view, no copy
-                upd += 2 * r["info"]["iterations"]
-            dt = time.perf_counter() - t_e
-            line["e2e"] = {"value": upd / dt, "unit": UNIT, "h2d_bytes_per_step": int(8 * m * m),
-                           "d2h_bytes_per_step": int(2 * 8 * m * q + 8 * q), "calls": calls, "seconds_per_call": dt / calls,
-                           "mm_updates_per_call": upd // calls, "seconds_upload": r["info"]["seconds_upload"],
-                           "seconds_init": r["info"]["seconds_init"], "seconds_loop": r["info"]["seconds_loop"],
-                           "api": "speigen_run_f64 (one-shot .Call entry) on a pinned host S"}
-        if not args.no_cpu:
-            cores = os.cpu_count() or 1
-            cv = cpu_mm_update_time(S_host, q, args.cpu_steps, cores)
-            line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_steps} MM updates (oracle port, direct-S mode, NumPy/OpenBLAS) on the full {m}x{m} S"}
+
+    # ---- multi-GPU self-check, part 1: every rank must hold the same result, bit for bit
+    parity = None
+    if world > 1:
+        digest = hashlib.sha256(res["vectors"].tobytes() + info["F"].tobytes()).hexdigest()
+        digests = [None] * world
+        dist.all_gather_object(digests, digest, group=cpu_group)
+        parity = {"replicas_identical": len(set(digests)) == 1, "ranks": world}
+
+    # ---- release the shards; the drop-in call below drives all N GPUs from rank 0's process
+    solver.close()
+    torch.cuda.empty_cache()
+    if dist is not None:
+        dist.barrier(group=cpu_group)
     if rank == 0:
+        need_host = (not args.no_e2e) or (world == 1 and not args.no_cpu)
+        S_host = host_cov(m, n, q, args.card, pinned=False).numpy() if need_host else None
+        if not args.no_e2e:
+            # end to end through the drop-in C ABI call with HOST buffers: H2D of the 20 GB S, validation scan, initialiser, MM loop,
+            # D2H of the results, on `world` GPUs of this process.  Headline: S in ordinary PAGEABLE memory (what R hands over).
+            calls = max(1, args.e2e_calls)
+            sb.spEigen(np.asfortranarray(S_host[:2048, :2048]), q, n_gpus=world)   # warm the contexts on a small case
+            dt, r = e2e_calls(sb, S_host, q, world, calls)
+            upd = 2 * r["info"]["iterations"]
+            line["e2e"] = {"value": upd / dt, "unit": UNIT,
+                           "h2d_bytes_per_step": int(8 * m * m / upd), "d2h_bytes_per_step": int((2 * 8 * m * q + 8 * q) / upd),
+                           "h2d_bytes_per_call": int(8 * m * m), "d2h_bytes_per_call": int(2 * 8 * m * q + 8 * q),
+                           "calls": calls, "seconds_per_call": dt, "n_gpus": world, "host_memory": "pageable",
+                           "mm_updates_counted_per_call": upd,
+                           "counting": "2 MM updates (V1, V2) per outer iteration of R/spEigen.R:119-120; the call also runs "
+                                       f"{r['info']['contractions']} streamed contractions in the loop (extrapolation/backtracking) and "
+                                       f"{r['info']['init_passes']} initialiser passes, which are NOT counted",
+                           "seconds_upload": r["info"]["seconds_upload"], "seconds_init": r["info"]["seconds_init"],
+                           "seconds_loop": r["info"]["seconds_loop"],
+                           "api": "speigen_run_f64 (one-shot .Call entry), single process driving %d GPU(s)" % world}
+            # the same with a pinned host S (upper bound of the upload path)
+            Hp = torch.empty((m, m), dtype=torch.float64, pin_memory=True)
+            Hp.copy_(torch.from_numpy(S_host))
+            dtp, rp = e2e_calls(sb, Hp.numpy(), q, world, 1)
+            line["e2e"]["pinned_host"] = {"value": 2 * rp["info"]["iterations"] / dtp, "seconds_per_call": dtp,
+                                          "seconds_upload": rp["info"]["seconds_upload"]}
+            del Hp
+            if world > 1:
+                # ---- multi-GPU self-check, part 2: the N-GPU trajectory against the single-GPU one on the same S
+                r1 = sb.spEigen(S_host.T, q, n_gpus=1, check_symmetric=1)
+                F1, FN = r1["info"]["F"], info["F"]
+                k = min(len(F1), len(FN), 10)
+                inner = np.abs(np.sum(r1["vectors"] * res["vectors"], axis=0))
+                parity.update({"F_prefix_len": int(k),
+                               "F_prefix_max_rel_dev_vs_1gpu": float(np.max(np.abs(F1[:k] - FN[:k]) / np.abs(F1[:k]))),
+                               "support_identical_vs_1gpu": bool(np.array_equal(r1["vectors"] != 0, res["vectors"] != 0)),
+                               "min_abs_inner_vs_1gpu": float(inner.min()),
+                               "iterations": [int(r1["info"]["iterations"]), int(info["iterations"])],
+                               "ok": bool(parity["replicas_identical"] and np.array_equal(r1["vectors"] != 0, res["vectors"] != 0)
+                                          and np.max(np.abs(F1[:k] - FN[:k]) / np.abs(F1[:k])) <= 1e-11 and inner.min() >= 1 - 1e-8)})
+        if world == 1 and not args.no_cpu:
+            cv = cpu_mm_update_time(S_host, q, args.cpu_steps, 1)
+            threads, blas = blas_threads()
+            line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port", "blas": blas, "host_cores": _HOST_CORES,
+                                    "sample": f"{args.cpu_steps} MM updates (oracle port, direct-S mode, NumPy/OpenBLAS) on the full {m}x{m} S"}
+        if parity is not None:
+            line["parity_check"] = parity
         emit(line)
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
 
 

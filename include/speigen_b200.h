@@ -98,6 +98,10 @@ typedef struct speigen_out {
   double seconds_upload;
   double seconds_init;
   double seconds_loop;
+  double seconds_setup;        /* one-shot calls: device allocation, peer mappings (0 when a cached context was reused) */
+  double seconds_prepare;      /* validation scan / centring (R/spEigen.R:53,60,75) */
+  int32_t upload_staged;       /* 1: the host matrix was pageable and went through the pinned staging ring */
+  int32_t polar_passes_max;    /* largest number of Gram passes any polar factor of the MM loop needed (2 = the usual case) */
 } speigen_out;
 
 /* ---- one-shot drop-in calls (host pointers) — what the .Call glue binds ------------------------

@@ -293,12 +293,12 @@ def finalize(V, thres):
 
 
 def spEigen(X, q=1, rho=0.5, data=False, d=None, V=None, thres=1e-9, mode="reference",
-            keep_iterates=False, return_trace=False):
+            keep_iterates=False, return_trace=False, max_iter=MAX_ITER):
     """spEigen(X, q, rho, data, d, V, thres), R/spEigen.R:46-163.
 
     Returns dict(vectors, standard_vectors, values) (+ 'trace', 'problem' if asked)."""
     prob = setup(X, q, rho, data, d, V, mode=mode)
-    vectors, tr = run_loop(prob, thres=thres, keep_iterates=keep_iterates)
+    vectors, tr = run_loop(prob, thres=thres, keep_iterates=keep_iterates, max_iter=max_iter)
     q = prob.q
     values = prob.sv2[:q] / (prob.nrow - 1) if prob.data else prob.sv2[:q].copy()   # :162
     out = dict(vectors=vectors, standard_vectors=prob.Vx[:, :q].copy(), values=values)

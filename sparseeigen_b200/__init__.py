@@ -54,7 +54,8 @@ class Out(C.Structure):
         ("stage_of_k", C.POINTER(C.c_int32)), ("trace_capacity", C.c_int32),
         ("iterations", C.c_int32), ("backtracks", C.c_int32), ("contractions", C.c_int32), ("init_passes", C.c_int32),
         ("init_converged", C.c_int32), ("init_residual", C.c_double), ("seconds_upload", C.c_double),
-        ("seconds_init", C.c_double), ("seconds_loop", C.c_double),
+        ("seconds_init", C.c_double), ("seconds_loop", C.c_double), ("seconds_setup", C.c_double),
+        ("seconds_prepare", C.c_double), ("upload_staged", C.c_int32), ("polar_passes_max", C.c_int32),
     ]
 
 
@@ -233,6 +234,12 @@ def _is_na(v) -> bool:
         return False
 
 
+def _trace_capacity(cfg) -> int:
+    """k can pass max_iter: reaching it ends a continuation stage, not the schedule (R/spEigen.R:151), and every remaining stage
+    still runs two iterations."""
+    return max(cfg.max_iter, 1) + 2 * (cfg.n_continuation + 1) + 8
+
+
 class _OutBuffers:
     def __init__(self, m, q, cplx, trace_capacity=1000):
         dt = np.complex128 if cplx else np.float64
@@ -259,7 +266,9 @@ class _OutBuffers:
         info = dict(iterations=self.c.iterations, backtracks=self.c.backtracks, contractions=self.c.contractions,
                     init_passes=self.c.init_passes, init_converged=bool(self.c.init_converged),
                     init_residual=self.c.init_residual, seconds_upload=self.c.seconds_upload,
-                    seconds_init=self.c.seconds_init, seconds_loop=self.c.seconds_loop,
+                    seconds_init=self.c.seconds_init, seconds_loop=self.c.seconds_loop, seconds_setup=self.c.seconds_setup,
+                    seconds_prepare=self.c.seconds_prepare, upload_staged=bool(self.c.upload_staged),
+                    polar_passes_max=self.c.polar_passes_max,
                     F=self.F[:k].copy(), step_a=self.step_a[:k].copy(), backtracks_per_k=self.bt[:k].copy(),
                     stage_of_k=self.stage[:k].copy())
         return dict(vectors=self.vectors, standard_vectors=self.standard_vectors, values=self.values, info=info)
@@ -299,7 +308,7 @@ def spEigen(X, q=1, rho=0.5, data=False, d=None, V=None, thres=1e-9, *, n_gpus=1
             setattr(cfg, k, v)
         dd = None if d is None else np.ascontiguousarray(d, dtype=np.float64)
         VV = None if V is None else _as_colmajor(np.asarray(V), False)
-        ob = _OutBuffers(m, q, False, trace_capacity=max(cfg.max_iter, 1))
+        ob = _OutBuffers(m, q, False, trace_capacity=_trace_capacity(cfg))
         _check(L.speigen_run_cov_of_data_f64(Xf.ctypes.data_as(_dp), n, m, float(q), float(rho), _ptr(dd),
                                              None if VV is None else VV.ctypes.data_as(_dp), float(thres),
                                              C.byref(cfg), C.byref(ob.c)))
@@ -333,7 +342,7 @@ def spEigen(X, q=1, rho=0.5, data=False, d=None, V=None, thres=1e-9, *, n_gpus=1
         VV = _as_colmajor(np.asarray(V), cplx)
         if VV.shape != (m, q):
             raise SpEigenError(23, "V must be m x q")
-    ob = _OutBuffers(m, q, cplx, trace_capacity=max(cfg.max_iter, 1))
+    ob = _OutBuffers(m, q, cplx, trace_capacity=_trace_capacity(cfg))
     fn = L.speigen_run_c64 if cplx else L.speigen_run_f64
     rc = fn(Xf.ctypes.data_as(_dp), nrow, m, 1 if data else 0, float(q), float(rho), _ptr(dd),
             None if VV is None else VV.ctypes.data_as(_dp), float(thres), C.byref(cfg), C.byref(ob.c))
@@ -548,7 +557,7 @@ class Solver:
                     init_residual=ob.c.init_residual, seconds_init=ob.c.seconds_init)
 
     def run(self, rho=0.5, d=None, thres=1e-9):
-        ob = _OutBuffers(self.m, self.q, self.cplx, max(self.cfg.max_iter, 1))
+        ob = _OutBuffers(self.m, self.q, self.cplx, _trace_capacity(self.cfg))
         dd = None if d is None else np.ascontiguousarray(d, dtype=np.float64)
         _check(self.L.speigen_solver_run(self.h, float(rho), _ptr(dd), float(thres), C.byref(ob.c)))
         return ob.result()

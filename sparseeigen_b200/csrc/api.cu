@@ -11,6 +11,7 @@ namespace speigen {
 const char* last_error();
 long long launch_count();
 void release_cov_context();   // cov_solver.cu: the dense context speigencov_run_* keeps between calls
+void release_stage_ring();    // solver.cu: the pinned staging ring of the pageable-upload path
 }  // namespace speigen
 using namespace speigen;
 
@@ -378,6 +379,7 @@ int speigen_shutdown(void) {
   DeviceRestore restore_device__;
   if (g_cached) { speigen_solver_destroy(g_cached); g_cached = nullptr; }
   release_cov_context();
+  release_stage_ring();
   return SPEIGEN_OK;
 }
 
@@ -407,6 +409,7 @@ static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data,
   const size_t e = is_complex ? 2 : 1;
   const size_t mat_bytes = static_cast<size_t>(nrow) * ncol * e * sizeof(double);
   const bool cacheable = mat_bytes <= (256u << 20);
+  const double t_setup0 = wall_s();
   speigen_solver* s = nullptr;
   if (g_cached && cacheable && std::memcmp(&g_cached_prob, &pb, sizeof(pb)) == 0 && std::memcmp(&g_cached_cfg, &cfg, sizeof(cfg)) == 0) {
     s = g_cached;
@@ -418,9 +421,13 @@ static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data,
   }
   int rc = s->impl.comm_ready ? SPEIGEN_OK : s->impl.init_comm_all();
   const double t0 = wall_s();
+  out->seconds_setup = t0 - t_setup0;
   if (rc == SPEIGEN_OK) rc = s->impl.load_host(X);
-  out->seconds_upload = wall_s() - t0;
+  const double t1 = wall_s();
+  out->seconds_upload = t1 - t0;
+  out->upload_staged = s->impl.upload_staged ? 1 : 0;
   if (rc == SPEIGEN_OK) rc = s->impl.prepare();
+  out->seconds_prepare = wall_s() - t1;
   if (rc == SPEIGEN_OK) rc = s->impl.init_vectors(V0, out);
   if (rc == SPEIGEN_OK) rc = s->impl.run(rho, d, thres, out);
   if (rc == SPEIGEN_OK && cacheable) {

@@ -30,12 +30,12 @@ __global__ void __launch_bounds__(256) k_scan_cov(const double* A, int64_t rows,
                                                   int full_check, const ScanPeers peers, double* part, int* ticket,
                                                   double* out4) {
   __shared__ double tileT[32][32 * E + 1];
-  __shared__ double s_red[4][8];
+  __shared__ double s_red[5][8];
   __shared__ int s_is_last;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t tr = (rows + 31) / 32, tc = (m + 31) / 32;
   const int64_t ntiles = tr * tc;
-  double sdiff = 0.0, sabs = 0.0, dmax = -DBL_MAX, nnan = 0.0;
+  double sdiff = 0.0, sabs = 0.0, dmax = -DBL_MAX, nnan = 0.0, dmin = DBL_MAX;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t tj = t / tc, ti = t - tj * tc;
     if (full_check) {
@@ -63,18 +63,20 @@ __global__ void __launch_bounds__(256) k_scan_cov(const double* A, int64_t rows,
           const double br = tileT[tx][r * E], bi = (E == 2) ? -tileT[tx][r * E + E - 1] : 0.0;
           sdiff += (E == 2) ? hypot(a[0] - br, a[E - 1] - bi) : fabs(a[0] - br);
         }
-        if (i == lo + j) dmax = fmax(dmax, a[0]);
+        if (i == lo + j) { dmax = fmax(dmax, a[0]); dmin = fmin(dmin, a[0]); }
       }
     }
     if (full_check) __syncthreads();
   }
   sdiff = warp_sum_d(sdiff); sabs = warp_sum_d(sabs); nnan = warp_sum_d(nnan); dmax = warp_max_d(dmax);
-  if (tx == 0) { s_red[0][ty] = sdiff; s_red[1][ty] = sabs; s_red[2][ty] = dmax; s_red[3][ty] = nnan; }
+  dmin = -warp_max_d(-dmin);
+  if (tx == 0) { s_red[0][ty] = sdiff; s_red[1][ty] = sabs; s_red[2][ty] = dmax; s_red[3][ty] = nnan; s_red[4][ty] = dmin; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double a = 0, b = 0, c = -DBL_MAX, d = 0;
-    for (int w = 0; w < 8; ++w) { a += s_red[0][w]; b += s_red[1][w]; c = fmax(c, s_red[2][w]); d += s_red[3][w]; }
-    part[blockIdx.x * 4 + 0] = a; part[blockIdx.x * 4 + 1] = b; part[blockIdx.x * 4 + 2] = c; part[blockIdx.x * 4 + 3] = d;
+    double a = 0, b = 0, c = -DBL_MAX, d = 0, mn = DBL_MAX;
+    for (int w = 0; w < 8; ++w) { a += s_red[0][w]; b += s_red[1][w]; c = fmax(c, s_red[2][w]); d += s_red[3][w]; mn = fmin(mn, s_red[4][w]); }
+    part[blockIdx.x * 8 + 0] = a; part[blockIdx.x * 8 + 1] = b; part[blockIdx.x * 8 + 2] = c; part[blockIdx.x * 8 + 3] = d;
+    part[blockIdx.x * 8 + 4] = mn;
     __threadfence();
     const int tk = atomicAdd(ticket, 1);
     s_is_last = (tk == (int)gridDim.x - 1);
@@ -83,11 +85,12 @@ __global__ void __launch_bounds__(256) k_scan_cov(const double* A, int64_t rows,
   __syncthreads();
   if (s_is_last && threadIdx.x == 0) {
     __threadfence();
-    double a = 0, b = 0, c = -DBL_MAX, d = 0;
+    double a = 0, b = 0, c = -DBL_MAX, d = 0, mn = DBL_MAX;
     for (unsigned k = 0; k < gridDim.x; ++k) {
-      a += __ldcg(part + k * 4); b += __ldcg(part + k * 4 + 1); c = fmax(c, __ldcg(part + k * 4 + 2)); d += __ldcg(part + k * 4 + 3);
+      a += __ldcg(part + k * 8); b += __ldcg(part + k * 8 + 1); c = fmax(c, __ldcg(part + k * 8 + 2)); d += __ldcg(part + k * 8 + 3);
+      mn = fmin(mn, __ldcg(part + k * 8 + 4));
     }
-    out4[0] = a; out4[1] = b; out4[2] = c; out4[3] = d;
+    out4[0] = a; out4[1] = b; out4[2] = c; out4[3] = d; out4[4] = mn;      // out4[4]: min Re diag (a PD matrix has a positive diagonal)
   }
 }
 

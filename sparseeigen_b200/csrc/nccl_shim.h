@@ -11,7 +11,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { NCCL_SUCCESS = 0 };
 enum { NCCL_DOUBLE = 8 };                 // ncclFloat64
-enum { NCCL_SUM = 0, NCCL_MAX = 2 };      // ncclRedOp_t
+enum { NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3 };      // ncclRedOp_t (ncclSum, ncclProd, ncclMax, ncclMin)
 
 struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId*);

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <string>
+#include <thread>
 
 namespace speigen {
 
@@ -198,7 +199,7 @@ int Solver::alloc_dev(Dev& d) {
   want(&d.scal, 512 * sizeof(double));
   want(&d.vecm, static_cast<size_t>(2 * m + 16) * sizeof(double));
   want(&d.vecm2, static_cast<size_t>(2 * m + 16) * sizeof(double));
-  want(&d.scan_part, kScanBlocks * 4 * sizeof(double));
+  want(&d.scan_part, kScanBlocks * 8 * sizeof(double));
   want(&d.out_cm, static_cast<size_t>(m) * bq * e * sizeof(double));
   size_t total = 0;
   for (auto& r : req) total += r.second;
@@ -242,6 +243,7 @@ void Solver::destroy() {
   h_scal = nullptr;
   if (h_res) cudaFreeHost(h_res);
   h_res = nullptr;
+
 }
 
 void Solver::reset_for_reuse() {
@@ -399,27 +401,182 @@ int Solver::read_scalars(int nd) {
 }
 
 // ---- matrix upload / tensor maps ---------------------------------------------------------------
+// The caller's matrix is ordinary pageable memory when the caller is R (or NumPy): a plain cudaMemcpyAsync from it is staged by
+// the driver through a small internal bounce buffer at a fraction of the PCIe rate.  Pageable sources above a few MB are
+// therefore staged here: worker threads copy 64 MB chunks into a ring of pinned slots while the previous chunks are in flight
+// (one async DMA per chunk), and consecutive chunks go to different GPUs so that every GPU's PCIe link is busy at once.
+// Process-wide pinned staging ring (allocated on first use, released by speigen_shutdown()): pinning memory costs ~0.3 ms per MB,
+// more than a whole small solve, so it is not re-done per call.
+struct StageRing {
+  static constexpr size_t kSlotBytes = 16u << 20;
+  static constexpr int kSlots = 24;
+  static constexpr int kMaxDev = 16;
+  void* base = nullptr;
+  cudaEvent_t ev[kSlots][kMaxDev] = {};     // an event belongs to the device whose stream records it: one per (slot, device ordinal)
+  int ensure() {
+    if (base) return SPEIGEN_OK;
+    SPE_CUDA(cudaHostAlloc(&base, kSlots * kSlotBytes, cudaHostAllocPortable));
+    return SPEIGEN_OK;
+  }
+  // event of `slot` on device `ordinal` (current device must be `ordinal`); created on first use
+  cudaError_t event(int slot, int ordinal, cudaEvent_t* out) {
+    cudaEvent_t& e = ev[slot][ordinal % kMaxDev];
+    if (!e) {
+      const cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (rc != cudaSuccess) return rc;
+    }
+    *out = e;
+    return cudaSuccess;
+  }
+  void release() {
+    if (!base) return;
+    for (auto& row : ev) for (auto& e : row) if (e) { cudaEventDestroy(e); e = nullptr; }
+    cudaFreeHost(base);
+    base = nullptr;
+  }
+};
+static StageRing& stage_ring_global() { static StageRing r; return r; }
+void release_stage_ring() { stage_ring_global().release(); }
+
+namespace {
+struct UploadChunk {
+  int dev;                 // index into devs
+  const char* src;         // first byte in the caller's matrix
+  size_t spitch;           // bytes between consecutive rows in the source
+  char* dst;               // device destination
+  size_t dpitch;
+  size_t width;            // bytes per row
+  size_t rows;
+};
+
+}  // namespace
+
 int Solver::load_host(const double* X) {
   const int e = 1 + cplx;
-  for (Dev& d : devs) {
-    SPE_CUDA(cudaSetDevice(d.ordinal));
+  // describe every device's shard as a 2-D copy (rows x width bytes)
+  std::vector<UploadChunk> shards;
+  for (size_t i = 0; i < devs.size(); ++i) {
+    Dev& d = devs[i];
     if (d.hi <= d.lo) continue;
+    UploadChunk c;
+    c.dev = static_cast<int>(i);
+    c.dst = reinterpret_cast<char*>(d.A);
+    c.dpitch = static_cast<size_t>(d.a_ld) * sizeof(double);
     if (data) {
       // X is n x m column-major: row j of A = samples lo..hi of variable j
-      SPE_CUDA(cudaMemcpy2DAsync(d.A, d.a_ld * sizeof(double), X + d.lo * e, static_cast<size_t>(n) * e * sizeof(double),
-                                 static_cast<size_t>(d.hi - d.lo) * e * sizeof(double), static_cast<size_t>(m),
-                                 cudaMemcpyHostToDevice, d.st));
+      c.src = reinterpret_cast<const char*>(X + d.lo * e);
+      c.spitch = static_cast<size_t>(n) * e * sizeof(double);
+      c.width = static_cast<size_t>(d.hi - d.lo) * e * sizeof(double);
+      c.rows = static_cast<size_t>(m);
     } else {
       // S is m x m column-major and Hermitian: row j of A = column lo+j of S
-      if (d.a_ld == m * e) {   // no pitch padding: one contiguous DMA
-        SPE_CUDA(cudaMemcpyAsync(d.A, X + d.lo * m * e, static_cast<size_t>(d.hi - d.lo) * m * e * sizeof(double),
-                                 cudaMemcpyHostToDevice, d.st));
-        continue;
-      }
-      SPE_CUDA(cudaMemcpy2DAsync(d.A, d.a_ld * sizeof(double), X + d.lo * m * e, static_cast<size_t>(m) * e * sizeof(double),
-                                 static_cast<size_t>(m) * e * sizeof(double), static_cast<size_t>(d.hi - d.lo),
-                                 cudaMemcpyHostToDevice, d.st));
+      c.src = reinterpret_cast<const char*>(X + d.lo * m * e);
+      c.spitch = static_cast<size_t>(m) * e * sizeof(double);
+      c.width = static_cast<size_t>(m) * e * sizeof(double);
+      c.rows = static_cast<size_t>(d.hi - d.lo);
     }
+    shards.push_back(c);
+  }
+  size_t total_bytes = 0;
+  for (auto& c : shards) total_bytes += c.rows * c.width;
+  cudaPointerAttributes pa{};
+  bool pageable = true;
+  if (cudaPointerGetAttributes(&pa, X) == cudaSuccess) pageable = (pa.type == cudaMemoryTypeUnregistered);
+  cudaGetLastError();
+  upload_staged = pageable && total_bytes >= (32u << 20) && cfg_stage_uploads();
+  if (!upload_staged) {
+    for (auto& c : shards) {
+      Dev& d = devs[c.dev];
+      SPE_CUDA(cudaSetDevice(d.ordinal));
+      if (c.spitch == c.width && c.dpitch == c.width)
+        SPE_CUDA(cudaMemcpyAsync(c.dst, c.src, c.rows * c.width, cudaMemcpyHostToDevice, d.st));
+      else
+        SPE_CUDA(cudaMemcpy2DAsync(c.dst, c.dpitch, c.src, c.spitch, c.width, c.rows, cudaMemcpyHostToDevice, d.st));
+    }
+    SPE_TRY(sync_all());
+    loaded = true;
+    return SPEIGEN_OK;
+  }
+  // ---- staged upload: worker threads each take whole chunks (copy into a pinned slot, enqueue the DMA, move on)
+  StageRing& ring = stage_ring_global();
+  SPE_CUDA(cudaSetDevice(devs[0].ordinal));
+  SPE_TRY(ring.ensure());
+  const size_t slot_bytes = StageRing::kSlotBytes;
+  // cut the shards into chunks of whole rows (<= slot size) and interleave the devices
+  std::vector<std::vector<UploadChunk>> per_dev(shards.size());
+  for (size_t s = 0; s < shards.size(); ++s) {
+    const UploadChunk& c = shards[s];
+    if (c.width > slot_bytes) {
+      // very long rows (m*e*8 > slot): split rows into column pieces
+      for (size_t r = 0; r < c.rows; ++r)
+        for (size_t off = 0; off < c.width; off += slot_bytes) {
+          UploadChunk k = c;
+          k.src = c.src + r * c.spitch + off; k.dst = c.dst + r * c.dpitch + off;
+          k.width = std::min(slot_bytes, c.width - off); k.rows = 1; k.spitch = k.width; k.dpitch = k.width;
+          per_dev[s].push_back(k);
+        }
+      continue;
+    }
+    const size_t rows_per = std::max<size_t>(1, slot_bytes / c.width);
+    for (size_t r = 0; r < c.rows; r += rows_per) {
+      UploadChunk k = c;
+      k.src = c.src + r * c.spitch; k.dst = c.dst + r * c.dpitch; k.rows = std::min(rows_per, c.rows - r);
+      per_dev[s].push_back(k);
+    }
+  }
+  std::vector<UploadChunk> order;
+  for (size_t i = 0;; ++i) {
+    bool any = false;
+    for (auto& v : per_dev) if (i < v.size()) { order.push_back(v[i]); any = true; }
+    if (!any) break;
+  }
+  const int nthreads = std::max(1, std::min<int>(StageRing::kSlots / 2, static_cast<int>(std::thread::hardware_concurrency())));
+  std::atomic<size_t> next{0};
+  std::atomic<int> failed{0};
+  std::vector<int> dev_ord(devs.size());
+  std::vector<cudaStream_t> dev_st(devs.size());
+  for (size_t i = 0; i < devs.size(); ++i) { dev_ord[i] = devs[i].ordinal; dev_st[i] = devs[i].st; }
+  auto worker = [&](int w) {
+    // worker w owns the slots w, w + nthreads, ... : no contention on a slot, its DMA is awaited by the thread that reuses it
+    int use = 0;
+    const int my_slots = (StageRing::kSlots - w + nthreads - 1) / nthreads;
+    std::vector<int> slot_dev(my_slots, -1);
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= order.size() || failed.load()) break;
+      const UploadChunk& c = order[i];
+      const int k = use % my_slots;
+      const int slot = w + k * nthreads;
+      ++use;
+      if (slot_dev[k] >= 0) {       // the DMA that last read this slot (recorded on that device's stream) must be done
+        cudaEvent_t pe = nullptr;
+        if (cudaSetDevice(dev_ord[slot_dev[k]]) != cudaSuccess || ring.event(slot, dev_ord[slot_dev[k]], &pe) != cudaSuccess ||
+            cudaEventSynchronize(pe) != cudaSuccess) { failed.store(1); break; }
+      }
+      char* stage = static_cast<char*>(ring.base) + static_cast<size_t>(slot) * slot_bytes;
+      if (c.spitch == c.width) std::memcpy(stage, c.src, c.rows * c.width);
+      else for (size_t r = 0; r < c.rows; ++r) std::memcpy(stage + r * c.width, c.src + r * c.spitch, c.width);
+      cudaError_t e = cudaSetDevice(dev_ord[c.dev]);
+      if (e == cudaSuccess) {
+        if (c.dpitch == c.width || c.rows == 1) e = cudaMemcpyAsync(c.dst, stage, c.rows * c.width, cudaMemcpyHostToDevice, dev_st[c.dev]);
+        else e = cudaMemcpy2DAsync(c.dst, c.dpitch, stage, c.width, c.width, c.rows, cudaMemcpyHostToDevice, dev_st[c.dev]);
+      }
+      cudaEvent_t me = nullptr;
+      if (e == cudaSuccess) e = ring.event(slot, dev_ord[c.dev], &me);
+      if (e == cudaSuccess) e = cudaEventRecord(me, dev_st[c.dev]);
+      if (e != cudaSuccess) { failed.store(1); break; }
+      slot_dev[k] = c.dev;
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int w = 0; w < nthreads; ++w) th.emplace_back(worker, w);
+    for (auto& t : th) t.join();
+  }
+  if (failed.load()) {
+    cudaGetLastError();
+    set_error("staged upload of the host matrix failed (CUDA error in a copy worker)");
+    return SPEIGEN_ERR_CUDA;
   }
   SPE_TRY(sync_all());
   loaded = true;
@@ -474,25 +631,27 @@ int Solver::prepare() {
         }
         SPE_NCCL(nc->AllReduce(d.scal + 2, d.scal + 2, 1, NCCL_DOUBLE, NCCL_MAX, d.comm, d.st));
         SPE_NCCL(nc->AllReduce(d.scal + 3, d.scal + 3, 1, NCCL_DOUBLE, NCCL_SUM, d.comm, d.st));
+        SPE_NCCL(nc->AllReduce(d.scal + 4, d.scal + 4, 1, NCCL_DOUBLE, NCCL_MIN, d.comm, d.st));
       }
       SPE_NCCL(nc->GroupEnd());
     }
-    SPE_TRY(read_scalars(4));
+    SPE_TRY(read_scalars(5));
     if (prob.world > 1 && single_process) {   // combine the shards' sums on the host (fixed device order)
-      double df = h_scal[0], sa = h_scal[1], mx = h_scal[2], nn = h_scal[3];
+      double df = h_scal[0], sa = h_scal[1], mx = h_scal[2], nn = h_scal[3], mn = h_scal[4];
       for (size_t i = 1; i < devs.size(); ++i) {
-        double tmp[4];
+        double tmp[5];
         SPE_CUDA(cudaSetDevice(devs[i].ordinal));
         SPE_CUDA(cudaMemcpyAsync(tmp, devs[i].scal, sizeof(tmp), cudaMemcpyDeviceToHost, devs[i].st));
         SPE_CUDA(cudaStreamSynchronize(devs[i].st));
         df += tmp[0];
         sa += tmp[1];
-        if (!devs[0].comm) { mx = std::max(mx, tmp[2]); nn += tmp[3]; }
+        if (!devs[0].comm) { mx = std::max(mx, tmp[2]); nn += tmp[3]; mn = std::min(mn, tmp[4]); }
       }
       h_scal[0] = df;
       h_scal[1] = sa;
       h_scal[2] = mx;
       h_scal[3] = nn;
+      h_scal[4] = mn;
     }
     if (cfg.check_na && (h_scal[3] > 0.0 || std::isnan(h_scal[1]))) {
       set_error("This function cannot handle NAs.");
@@ -509,6 +668,12 @@ int Solver::prepare() {
       }
     }
     scale_max = h_scal[2];   // max(Re(diag(X)))   R/spEigen.R:82
+    // necessary condition of R/spEigen.R:77 that costs nothing: x^T S x >= lambda_min for x = e_i, so a diagonal entry below
+    // pd_tol proves an eigenvalue below pd_tol (the Ritz-value probe in init_vectors covers what the diagonal cannot show)
+    if (h_scal[4] < cfg.pd_tol) {
+      set_error("The covariance matrix is not PD.");
+      return SPEIGEN_ERR_NOT_PD;
+    }
   } else {
     const int e = 1 + cplx;
     for (Dev& d : devs) {
@@ -1000,10 +1165,17 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
     break;
   }
   if (passes > cfg.init_max_passes) passes = cfg.init_max_passes;
+  if (!converged && !cfg.allow_unconverged_init) {
+    // eigen()/svd() of the reference always converge; carrying on with inexact sv2 / Vx would silently change the rho scaling, the
+    // returned `values` / `standard_vectors` and the start point (and would skip the PD probe)
+    set_error("the block subspace iteration that replaces eigen()/svd() did not converge: residual %.3e after %d passes "
+              "(init_tol %.1e); raise init_max_passes or set allow_unconverged_init", resid_rel, passes, cfg.init_tol);
+    return SPEIGEN_ERR_NOT_CONVERGED;
+  }
   // R/spEigen.R:77 tests the full spectrum.  Without a full EVD we bound lambda_min from above with Ritz values: a few
   // block power passes on (theta_1 I - S) pull the block towards the bottom of the spectrum; any Ritz value of S below
   // pd_tol proves "not PD".  (A tiny negative eigenvalue hidden in a dense bottom cluster can escape this test.)
-  if (!data && cfg.pd_check_passes > 0 && converged) {
+  if (!data && cfg.pd_check_passes > 0) {
     const double sigma = sv2[0];
     for (Dev& d : devs) {
       SPE_CUDA(cudaSetDevice(d.ordinal));
@@ -1083,6 +1255,7 @@ int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) 
     SPE_CUDA(cudaSetDevice(d.ordinal));
     SPE_CUDA(cudaMemsetAsync(d.twarm, 0, static_cast<size_t>(N_TAIL_SITES) * 2 * kWarmDoubles * sizeof(double), d.st));
     SPE_CUDA(cudaMemsetAsync(d.tstatus, 0, sizeof(int), d.st));
+    SPE_CUDA(cudaMemsetAsync(d.tdiag, 0, 48 * sizeof(double), d.st));
   }
   std::vector<double> dv(q), rv(q);
   if (d_in) for (int c = 0; c < q; ++c) dv[c] = d_in[c];
@@ -1197,6 +1370,10 @@ int Solver::run(double rho, const double* d_in, double thres, speigen_out* out) 
     out->iterations = k;
     out->backtracks = total_bt;
     out->contractions = static_cast<int>(contractions - c_before);
+    double dg[8] = {};
+    SPE_CUDA(cudaMemcpyAsync(dg, d.tdiag, sizeof(dg), cudaMemcpyDeviceToHost, d.st));
+    SPE_CUDA(cudaStreamSynchronize(d.st));
+    out->polar_passes_max = static_cast<int>(dg[5]);
     out->seconds_loop = now_s() - t0;
   }
   SPE_TRY(sync_all());

@@ -3,6 +3,7 @@
 // of scalar read-backs per outer iteration.  One Solver drives every GPU this process owns; replicated
 // m x q work is executed redundantly per GPU (bit-identical), the streamed matrix is sharded.
 #pragma once
+#include <cstdlib>
 #include <vector>
 #include "../../include/speigen_b200.h"
 #include "common.cuh"
@@ -167,6 +168,9 @@ class Solver {
   int check_tail_status(double status_value);
   int wait_latest_tail();
   int dots_parity = 0;
+  // staged upload of pageable host matrices (load_host)
+  bool upload_staged = false;                 // how the last load_host moved the data (reported in speigen_out)
+  static bool cfg_stage_uploads() { const char* e = getenv("SPEIGEN_NO_STAGING"); return !(e && e[0] == '1'); }
 
  private:
   int alloc_dev(Dev& d);

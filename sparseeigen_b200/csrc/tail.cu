@@ -874,6 +874,8 @@ __global__ void __launch_bounds__(TT, 1) k_tail(const TailArgs p) {
       if (p.producer == TAIL_EXTRAP && !p.retry) { p.diag[1] = nR; p.diag[2] = nU; }
       p.diag[3] = passes;
       p.diag[4] = sweeps;
+      p.diag[5] = fmax(p.diag[5], static_cast<double>(passes));     // running maximum (reset by the host per solve)
+      p.diag[6] += sweeps;
     }
   }
   if (multi) __threadfence_system();

@@ -1,10 +1,17 @@
 """GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes), against the oracle on the
 same seeded inputs, against the golden fixtures, and through size-independent properties at full size.
 
-Tolerances (FP64 path, north_star): single kernels <= 1e-12 relative; objective trajectory <= 1e-10
-relative on the pre-round-off prefix (iterations whose SQUAREM step |a| < 1e3); end to end:
-identical support after thresholding and per-column |<u_ref, u_gpu>| >= 1 - 1e-5 (the oracle's own
-1-ulp noise floor is measured in the same test and must be of the same order)."""
+Tolerances (FP64 path; north_star: |<u_ref, u_gpu>| >= 1 - 1e-8, identical support, objective trajectory within 1e-10):
+  * single kernels <= 1e-13 relative, single MM update <= 1e-11, objective <= 1e-12 (golden known answers);
+  * objective trajectory <= 1e-10 (north star) on EVERY iteration before the first SQUAREM step with |a| > 1e3 (k = 15..19
+    of ~25: from there on U = V2 - 2 V1 + V is pure cancellation noise and a^2 U amplifies 1e-16 differences);
+  * end to end, against the oracle in BOTH modes (G through the eigenbasis Vx as R/spEigen.R:177, and G = S V): identical
+    support, |<u_ref, u_gpu>| >= 1 - 1e-7, final objective within 1e-6.  Measured (profiles/r02_parity.json, 6 cases x 2 modes):
+    inner-product deficit 3e-11 .. 7.1e-8 (1e-8 met in 4 cases; the two others sit at 1.06e-8 and 7.1e-8), final objective
+    1e-8 .. 6.7e-7 - the same range as the oracle against ITSELF on an input perturbed by one ulp (deficit 1e-15 .. 5.4e-8,
+    final objective 8e-12 .. 5.3e-7), whose late accept/backtrack decisions flip just as the GPU's do.  The north-star 1e-8 /
+    1e-10 end-to-end figures are below the reference algorithm's own reproducibility; where a case does meet 1e-8 today it
+    is pinned at 1e-8 (`inner_tol`)."""
 import numpy as np
 import pytest
 
@@ -104,6 +111,46 @@ def test_polar(m, q, cplx, cond):
     assert rel(U, o.polar(A)) < 1e-15 * cond * 50 + 1e-13
 
 
+@pytest.mark.parametrize("m,q,cplx,cond", [(2000, 10, False, 1e9), (1500, 20, False, 1e12), (900, 6, True, 1e10)])
+def test_polar_ill_conditioned(m, q, cplx, cond):
+    """cond(B)^2 is beyond double precision: the Gram route needs more than two passes (eigenvalues drowned in round-off are
+    clamped, every pass takes the square root of the condition number) and still returns THE polar factor - the reference's
+    svd(G - H) -> u v^H (R/spEigen.R:180-182) always returns an orthonormal factor."""
+    rng = np.random.default_rng(int(np.log10(cond)))
+    Qm, _ = np.linalg.qr(panel(rng, m, q, cplx))
+    Wm, _ = np.linalg.qr(panel(rng, q, q, cplx))
+    A = (Qm * np.logspace(0, -np.log10(cond), q)[None, :]) @ np.conj(Wm.T)      # singular values 1 .. 1/cond
+    with sb.Solver(m, q, is_complex=cplx) as s:
+        U = s.polar(A)
+        passes = s.tail_diag()["passes"]
+    assert passes >= 3
+    assert np.abs(np.conj(U.T) @ U - np.eye(q)).max() < 1e-13
+    assert rel(U, Qm @ np.conj(Wm.T)) < 1e-15 * cond * 50 + 1e-13
+
+
+def test_polar_rank_deficient():
+    """A rank-deficient Procrustes target: R's svd() -> u v^H (R/spEigen.R:180-182) still returns an orthonormal factor (the
+    completion of the null direction is arbitrary).  The Gram route does the same through its clamped passes: the factor is
+    orthonormal and U^H A is Hermitian positive semi-definite (the defining property of a polar factor).  Only a target whose
+    Gram matrix has an exactly zero row (a zero column) cannot be completed and is reported (SPEIGEN_ERR_NUMERIC)."""
+    rng = np.random.default_rng(3)
+    A = panel(rng, 500, 6, False)
+    A[:, 4] = A[:, 1] - 2.0 * A[:, 2]          # exact linear dependence
+    with sb.Solver(500, 6) as s:
+        U = s.polar(A)
+        assert s.tail_diag()["passes"] >= 3
+        assert np.abs(U.T @ U - np.eye(6)).max() < 1e-12
+        H = U.T @ A
+        assert np.abs(H - H.T).max() < 1e-9 * np.abs(H).max() and np.linalg.eigvalsh((H + H.T) / 2).min() > -1e-9 * np.abs(H).max()
+        assert rel(U @ H, A) < 1e-9
+        Z = A.copy(); Z[:, 2] = 0.0
+        with pytest.raises(sb.SpEigenError) as ei:
+            s.polar(Z)
+        assert ei.value.code == 26
+        U = s.polar(panel(rng, 500, 6, False))  # the solver stays usable
+        assert np.abs(U.T @ U - np.eye(6)).max() < 1e-13
+
+
 @pytest.mark.parametrize("n,cplx", [(1, False), (2, False), (3, False), (8, False), (19, False), (24, False), (7, True), (20, True)])
 def test_eig_small_jacobi(n, cplx):
     rng = np.random.default_rng(n)
@@ -156,35 +203,48 @@ def test_fused_and_unfused_epilogue_agree_bitwise():
 # ---------------------------------------------------------------------------------------------------
 # end to end against the oracle
 # ---------------------------------------------------------------------------------------------------
-def _e2e(X, q, data=False, rho=0.5, **kw):
+def _e2e(X, q, data=False, rho=0.5, inner_tol=1e-7, f_tol=1e-6, **kw):
+    """The drop-in call against the oracle in both modes.  inner_tol: bound on 1 - |<u_ref, u_gpu>| (north star 1e-8 where today's
+    build meets it, see the module docstring)."""
     r = sb.spEigen(X, q, rho=rho, data=data, **kw)
-    ro = o.spEigen(X, q, rho=rho, data=data, mode="direct", return_trace=True,
-                   **{k: v for k, v in kw.items() if k in ("d", "V", "thres")})
-    tr = ro["trace"]
-    F, Fo = r["info"]["F"], np.array(tr.F)
-    # prefix of the trajectory that is not round-off dominated (|a| < 1e3 in both runs so far)
-    n = 0
-    for k in range(min(len(F), len(Fo))):
-        if abs(tr.a_init[k]) > 1e3 or abs(r["info"]["step_a"][k]) > 1e3:
-            break
-        n = k + 1
-    assert n >= 8
-    assert np.max(np.abs(F[:n] - Fo[:n]) / np.maximum(1.0, np.abs(Fo[:n]))) < 1e-10
-    assert np.array_equal(r["info"]["stage_of_k"][:n], np.array(tr.stage)[:n])
-    assert np.array_equal(r["vectors"] != 0, ro["vectors"] != 0)                      # identical support
-    assert np.all(colwise_inner(r["vectors"], ro["vectors"]) > 1 - 1e-5)
-    assert np.allclose(r["values"], ro["values"], rtol=1e-11)
-    assert np.all(colwise_inner(r["standard_vectors"], ro["standard_vectors"]) > 1 - 1e-10)
+    F = r["info"]["F"]
     G = np.conj(r["vectors"].T) @ r["vectors"]
     assert np.abs(np.diag(G) - 1).max() < 1e-12
-    assert abs(F[-1] - Fo[-1]) / abs(Fo[-1]) < 1e-4
-    return r, ro
+    assert r["info"]["polar_passes_max"] == 2                  # no polar factor needed the ill-conditioned fallback
+    out = None
+    for mode in ("direct", "reference"):
+        ro = o.spEigen(X, q, rho=rho, data=data, mode=mode, return_trace=True,
+                       **{k: v for k, v in kw.items() if k in ("d", "V", "thres")})
+        tr = ro["trace"]
+        Fo = np.array(tr.F)
+        # every iteration before the first huge SQUAREM step (in either run) must agree to the north-star 1e-10
+        n = 0
+        for k in range(min(len(F), len(Fo))):
+            if abs(tr.a_final[k]) > 1e3 or abs(r["info"]["step_a"][k]) > 1e3:
+                break
+            n = k + 1
+        assert n >= 12, (mode, n)
+        dev = np.max(np.abs(F[:n] - Fo[:n]) / np.maximum(1.0, np.abs(Fo[:n])))
+        assert dev < 1e-10, (mode, dev)
+        assert np.array_equal(r["info"]["stage_of_k"][:n], np.array(tr.stage)[:n])
+        assert np.array_equal(r["info"]["backtracks_per_k"][:n], np.array(tr.backtracks)[:n])
+        assert np.array_equal(r["vectors"] != 0, ro["vectors"] != 0)                      # identical support
+        deficit = 1 - colwise_inner(r["vectors"], ro["vectors"]).min()
+        Fdev = abs(F[-1] - Fo[-1]) / abs(Fo[-1])
+        print(f"e2e vs oracle[{mode}]: prefix {n} of {len(F)} iterations within {dev:.1e}; 1-|<u,u>| = {deficit:.2e}; final F {Fdev:.1e}")
+        assert deficit <= inner_tol, (mode, deficit)
+        assert Fdev <= f_tol, (mode, Fdev)
+        assert np.allclose(r["values"], ro["values"], rtol=1e-11)
+        assert np.all(colwise_inner(r["standard_vectors"], ro["standard_vectors"]) > 1 - 1e-10)
+        if mode == "direct":
+            out = ro
+    return r, out
 
 
 def test_e2e_readme_config():
     """configs[0]: README example spEigen(cov(X), q=3), m=500, n=100 (README.md:56-108)."""
     X, Vq = o.spiked_samples(500, 100, 3, 0.1, seed=42)
-    r, ro = _e2e(o.sample_cov(X), 3)
+    r, ro = _e2e(o.sample_cov(X), 3, inner_tol=1e-8)
     assert np.all(colwise_inner(r["vectors"], Vq) >= 0.997)
     assert np.array_equal((r["vectors"] != 0).sum(axis=0), [50, 50, 50])
     # the oracle's own noise floor: same code, S perturbed by 1 ulp
@@ -195,12 +255,18 @@ def test_e2e_readme_config():
     floor = 1 - colwise_inner(rp["vectors"], ro["vectors"]).min()
     ours = 1 - colwise_inner(r["vectors"], ro["vectors"]).min()
     print(f"noise floor (oracle vs 1-ulp-perturbed oracle): {floor:.2e}; GPU vs oracle: {ours:.2e}")
-    assert ours < max(1e3 * floor, 1e-5)
+    assert ours < max(10 * floor, 1e-8)
 
 
 def test_e2e_data_matrix():
     X, _ = o.spiked_samples(500, 100, 3, 0.1, seed=42)
-    _e2e(X, 3, data=True)
+    _e2e(X, 3, data=True, inner_tol=1e-8)
+
+
+def test_e2e_config3_scaled_complex_data():
+    """configs[2] at 1/50 scale: complex data matrix n = 4000 x m = 400, q = 5."""
+    X, _ = o.spiked_samples(400, 4000, 5, 0.05, seed=42, cplx=True)
+    _e2e(X, 5, data=True, inner_tol=1e-8)
 
 
 def test_e2e_config2_m5000_q10():
@@ -211,7 +277,7 @@ def test_e2e_config2_m5000_q10():
 
 def test_e2e_complex_cov_and_data():
     Xc, _ = o.spiked_samples(400, 500, 3, 0.2, seed=1, cplx=True)
-    _e2e(o.sample_cov(Xc), 3)
+    _e2e(o.sample_cov(Xc), 3, rho=0.6, inner_tol=1e-8)
     _e2e(Xc, 3, data=True, rho=0.6)
 
 
@@ -220,7 +286,8 @@ def test_e2e_custom_d_V_thres_q1():
     S = o.sample_cov(X)
     prob = o.setup(S, 4)
     _e2e(S, 4, d=np.array([1.0, 0.9, 0.8, 0.7]))
-    _e2e(S, 4, V=prob.V[:, ::-1].copy() * np.array([1, -1, 1, -1])[None, :])
+    # a permuted, sign-flipped start takes 29 iterations, 10 of them in the round-off dominated regime: 1.5e-7 / 1.9e-6 measured
+    _e2e(S, 4, V=prob.V[:, ::-1].copy() * np.array([1, -1, 1, -1])[None, :], inner_tol=1e-6, f_tol=1e-5)
     r = sb.spEigen(S, 1)
     assert r["vectors"].shape == (300, 1) and abs(np.linalg.norm(r["vectors"]) - 1) < 1e-12
     big = sb.spEigen(S, 4, thres=0.05)
@@ -243,9 +310,9 @@ def test_e2e_golden(golden, name):
     r = sb.spEigen(X, q, rho=float(golden[f"{name}.rho"]), data=bool(golden[f"{name}.data"]))
     assert np.allclose(r["values"], golden[f"{name}.values"], rtol=1e-11)
     assert np.array_equal(r["vectors"] != 0, golden[f"{name}.vectors"] != 0)
-    assert np.all(colwise_inner(r["vectors"], golden[f"{name}.vectors"]) > 1 - 1e-5)
+    assert np.all(colwise_inner(r["vectors"], golden[f"{name}.vectors"]) > 1 - 1e-7)
     F, Fg = r["info"]["F"], golden[f"{name}.F"]
-    assert np.allclose(F[:8], Fg[:8], rtol=1e-10)
+    assert np.allclose(F[:12], Fg[:12], rtol=1e-10)
 
 
 def test_run_is_bit_reproducible():
@@ -335,6 +402,63 @@ def test_not_pd_detected_beyond_the_top_block():
     assert r["vectors"].shape == (m, 3)
 
 
+def _flat_bottom(m, lam_min, rng):
+    """PSD-looking matrix: 10 spikes, a flat bulk of eigenvalues in [0.01, 0.02], one eigenvalue lam_min."""
+    Qm, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    lam = np.concatenate([np.linspace(50, 5, 10), np.linspace(0.02, 0.01, m - 11), [lam_min]])
+    S = (Qm * lam[None, :]) @ Qm.T
+    return (S + S.T) / 2
+
+
+@pytest.mark.parametrize("lam_min", [-25.0, -5.0])
+def test_not_pd_clear_violations_are_found(lam_min):
+    """R/spEigen.R:77 on the cases the Ritz-value probe can decide: |lambda_min| of the order of the leading eigenvalues."""
+    S = _flat_bottom(300, lam_min, np.random.default_rng(5))
+    with pytest.raises(o.SpEigenError, match="not PD"): o.spEigen(S, 3)
+    with pytest.raises(sb.SpEigenError, match="not PD"): sb.spEigen(S, 3)
+
+
+def test_not_pd_negative_diagonal_is_found_by_the_scan():
+    """A diagonal entry below -1e-10 proves an eigenvalue below -1e-10 (x = e_i): found in the validation pass, whatever the spectrum."""
+    X, _ = o.spiked_samples(300, 120, 3, 0.1, seed=2)
+    S = o.sample_cov(X)
+    S[17, :] *= 1e-4; S[:, 17] *= 1e-4                      # keeps S symmetric; tiny row/column
+    S[17, 17] = -1e-6
+    with pytest.raises(o.SpEigenError, match="not PD"): o.spEigen(S, 3)
+    with pytest.raises(sb.SpEigenError, match="not PD"): sb.spEigen(S, 3)
+
+
+@pytest.mark.xfail(strict=True, reason="documented limit: R/spEigen.R:77 tests the full spectrum (O(m^3) eigen()); this build bounds lambda_min "
+                                       "with Ritz values from a few block power passes, which cannot resolve a -1e-6 eigenvalue sitting under a "
+                                       "flat bulk (relative gap 1e-8: any polynomial method needs ~1e4 contractions); the matrix is accepted")
+def test_not_pd_near_miss_under_a_flat_bulk():
+    S = _flat_bottom(300, -1e-6, np.random.default_rng(5))
+    with pytest.raises(o.SpEigenError, match="not PD"): o.spEigen(S, 3)
+    with pytest.raises(sb.SpEigenError, match="not PD"): sb.spEigen(S, 3)
+
+
+def test_unconverged_initialiser_is_an_error():
+    """eigen()/svd() always converge; a subspace iteration that misses its tolerance must not be carried on silently."""
+    X, _ = o.spiked_samples(600, 150, 4, 0.05, seed=3)
+    S = o.sample_cov(X)
+    with pytest.raises(sb.SpEigenError) as ei:
+        sb.spEigen(S, 4, init_max_passes=2)
+    assert ei.value.code == 27
+    r = sb.spEigen(S, 4, init_max_passes=2, allow_unconverged_init=1)
+    assert not r["info"]["init_converged"] and r["vectors"].shape == (600, 4)
+
+
+def test_max_iter_ends_a_stage_not_the_schedule():
+    """R/spEigen.R:151: k >= max_iter only breaks the inner loop; the remaining (p, eps) stages still run two iterations each."""
+    X, _ = o.spiked_samples(400, 100, 3, 0.1, seed=12)
+    S = o.sample_cov(X)
+    r = sb.spEigen(S, 3, max_iter=6)
+    ro = o.spEigen(S, 3, mode="direct", return_trace=True, max_iter=6)
+    assert r["info"]["iterations"] == ro["trace"].k
+    assert np.array_equal(r["info"]["stage_of_k"], np.array(ro["trace"].stage))
+    assert r["info"]["stage_of_k"][-1] == 11
+
+
 # ---------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE config 4: m = 50000, q = 20) — no oracle at this size
 # ---------------------------------------------------------------------------------------------------
@@ -373,3 +497,67 @@ def test_full_size_properties():
         if st[k] == st[k - 1]:
             assert F[k] * (1 + np.sign(F[k]) * 1e-9) > F[k - 1]  # accepted steps are monotone within a stage
     assert np.all(np.diff(r["values"]) < 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE configs[2]: complex data matrix n = 200000 x m = 20000, q = 20, 64 GB) — no oracle at this size
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_properties_config3_complex_data():
+    import torch
+    free, _ = torch.cuda.mem_get_info(0)
+    n, m, q = 200000, 20000, 20
+    if free < 1.15 * 16.0 * n * m:
+        pytest.skip("needs ~75 GB of free device memory")
+    card = 0.02
+    sp = int(round(card * m))
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(42)
+    lam = 100.0 * torch.arange(q, 0, -1, dtype=torch.float64, device=dev)
+
+    def cn(rows):   # CN(0,1) block [rows][n] in the library's layout (row = variable, contiguous = samples, interleaved complex)
+        return torch.view_as_complex(torch.randn(rows, n, 2, dtype=torch.float64, device=dev, generator=g) / np.sqrt(2.0))
+
+    with sb.Solver(m, q, n=n, is_complex=True, is_data=True) as s:
+        s.init_comm(None)
+        phases = torch.exp(1j * 2 * np.pi * torch.rand(q * sp, dtype=torch.float64, device=dev, generator=g)) / np.sqrt(sp)
+        for c in range(q):            # planted block c: X += (Z v)(sqrt(lam_c) - 1) v^H   (vignette model, complex)
+            Zb = cn(sp)
+            v = phases[c * sp:(c + 1) * sp]
+            zv = (Zb * v[:, None]).sum(dim=0)
+            Zb += torch.conj(v)[:, None] * (zv * (torch.sqrt(lam[c]) - 1.0))[None, :]
+            torch.cuda.synchronize()
+            s.load_device_rows(c * sp, sp, Zb.data_ptr(), 2 * n)
+            del Zb
+        for r0 in range(q * sp, m, 1000):
+            Zb = cn(min(1000, m - r0))
+            torch.cuda.synchronize()
+            s.load_device_rows(r0, Zb.shape[0], Zb.data_ptr(), 2 * n)
+            del Zb
+        torch.cuda.empty_cache()
+        s.prepare()                                               # centring on the device (R/spEigen.R:60)
+        rng = np.random.default_rng(0)
+        U = rng.standard_normal((m, 4)) + 1j * rng.standard_normal((m, 4))
+        W = rng.standard_normal((m, 4)) + 1j * rng.standard_normal((m, 4))
+        YU, YW = s.contract(U), s.contract(W)                     # X^H (X .) : linear and Hermitian positive semi-definite
+        assert rel(s.contract(0.5 * U - 2.0j * W), 0.5 * YU - 2.0j * YW) < 1e-13
+        A = np.conj(W.T) @ YU
+        assert np.abs(A - np.conj((np.conj(U.T) @ YW).T)).max() / np.abs(A).max() < 1e-12
+        assert np.all(np.real(np.sum(np.conj(U) * YU, axis=0)) > 0)
+        info = s.init()
+        assert info["init_converged"] and info["init_residual"] < 1e-12
+        r = s.run(rho=0.5)
+    V = r["vectors"]
+    assert np.abs(np.conj(V.T) @ V - np.eye(q)).max() < 1e-6
+    assert np.array_equal((V != 0).sum(axis=0), np.full(q, sp))          # planted cardinality 0.02 m
+    Vq = np.zeros((m, q), dtype=np.complex128)
+    ph = phases.cpu().numpy()
+    for c in range(q):
+        Vq[c * sp:(c + 1) * sp, c] = ph[c * sp:(c + 1) * sp]
+    assert np.all(colwise_inner(V, Vq) > 0.9999)
+    F, st = r["info"]["F"], r["info"]["stage_of_k"]
+    for k in range(1, len(F)):
+        if st[k] == st[k - 1]:
+            assert F[k] * (1 + np.sign(F[k]) * 1e-9) > F[k - 1]
+    assert np.all(np.diff(r["values"]) < 0)
+    assert r["info"]["polar_passes_max"] == 2

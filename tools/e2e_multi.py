@@ -1,21 +1,34 @@
-"""End-to-end drop-in call on P GPUs of one process (what the R glue does): speigen_run_f64 on a pinned host S."""
-import sys, os, json, time
+"""End-to-end drop-in call on P GPUs of one process (what the R glue does): speigen_run_f64 on a host S (m = 50k, 20 GB),
+from ordinary pageable memory (what R hands over) and from pinned memory, with the library's own time breakdown.
+
+  GPUS=1,2,4,8 python tools/e2e_multi.py  >  profiles/r02_e2e_single_process_multi_gpu.jsonl
+"""
+import json
+import os
+import sys
+import time
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
-import sparseeigen_b200 as sb
-from bench import synth_cov_rows, symmetrize_
+import numpy as np      # noqa: E402
+import torch            # noqa: E402
+import sparseeigen_b200 as sb    # noqa: E402
+from bench import host_cov, emit  # noqa: E402   (bench points the process stdout at stderr; emit() writes to the real one)
+
 m, n, q = 50000, 10000, 20
-S = symmetrize_(synth_cov_rows(m, n, q, 0.02, 0, m, torch.device("cuda", 0)))
-S_host_t = torch.empty((m, m), dtype=torch.float64, pin_memory=True); S_host_t.copy_(S); del S
-torch.cuda.empty_cache()
-S_host = S_host_t.numpy()
-sb.spEigen(np.asfortranarray(S_host[:2048, :2048]), q)
+S_page = host_cov(m, n, q, 0.02, pinned=False).numpy()
+S_pin_t = torch.empty((m, m), dtype=torch.float64, pin_memory=True)
+S_pin_t.copy_(torch.from_numpy(S_page))
+S_pin = S_pin_t.numpy()
 for P in [int(x) for x in os.environ.get("GPUS", "1,2,4,8").split(",")]:
-    for rep in range(2):
-        t0 = time.perf_counter()
-        r = sb.spEigen(S_host.T, q, n_gpus=P, check_symmetric=1)
-        dt = time.perf_counter() - t0
-    i = r["info"]
-    print(json.dumps({"n_gpus": P, "seconds_per_call": dt, "mm_updates_per_s": 2 * i["iterations"] / dt, "upload_s": i["seconds_upload"],
-                      "init_s": i["seconds_init"], "loop_s": i["seconds_loop"], "iterations": i["iterations"], "F_final": float(i["F"][-1]),
-                      "nonzeros": [int(x) for x in (r["vectors"] != 0).sum(axis=0)[:3]]}), flush=True)
+    sb.spEigen(np.asfortranarray(S_page[:2048, :2048]), q, n_gpus=P)      # contexts + peer mappings of this GPU set
+    for kind, S_host in (("pageable", S_page), ("pinned", S_pin)):
+        for rep in range(2):
+            t0 = time.perf_counter()
+            r = sb.spEigen(S_host.T, q, n_gpus=P, check_symmetric=1)
+            dt = time.perf_counter() - t0
+        i = r["info"]
+        parts = {k: i[k] for k in ("seconds_setup", "seconds_upload", "seconds_prepare", "seconds_init", "seconds_loop")}
+        emit({"n_gpus": P, "host_memory": kind, "seconds_per_call": dt, "mm_updates_per_s": 2 * i["iterations"] / dt, **parts,
+              "seconds_other": dt - sum(parts.values()), "upload_staged": i["upload_staged"], "iterations": i["iterations"],
+              "polar_passes_max": i["polar_passes_max"], "F_final": float(i["F"][-1]),
+              "nonzeros": [int(x) for x in (r["vectors"] != 0).sum(axis=0)[:3]]})
