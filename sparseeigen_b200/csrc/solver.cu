@@ -875,18 +875,14 @@ int Solver::op_contract(Buf in, const PanelDims& pd, Buf outY, Buf outB, Buf vep
 }
 
 // ---- polar factor (K3 + applies):  out = in (in^H in)^{-1/2}, two Gram passes ------
-int Solver::op_polar(Buf in, Buf out, const PanelDims& pd, bool have_gram, double* /*unused*/, int which_absmin, int warm_slot) {
-  for (Dev& d : devs) {
-    SPE_CUDA(cudaSetDevice(d.ordinal));
-    if (!have_gram) SPE_TRY(launch_gram(pd, d.buf[in], d.buf[in], d.ps.gram_part, d.st));
-    double* warm = (warm_slot >= 0) ? d.warm + static_cast<size_t>(warm_slot) * kWarmStride : nullptr;
-    SPE_TRY(launch_small(pd, d.ps.gram_part, pd.nblk, SMALL_INVSQRT, d.Msmall, d.evals, d.status, warm, d.st));
-    SPE_TRY(launch_apply(pd, d.buf[in], d.Msmall, d.buf[BT2], d.gram_part2, nullptr, d.ps.ticket, d.st));
-    SPE_TRY(launch_small(pd, d.gram_part2, pd.nblk, SMALL_INVSQRT, d.Msmall, d.evals, d.status, nullptr, d.st));
-    double* am = which_absmin == 1 ? d.absmin_a : (which_absmin == 2 ? d.absmin_b : nullptr);
-    SPE_TRY(launch_apply(pd, d.buf[BT2], d.Msmall, d.buf[out], nullptr, am, d.ps.ticket, d.st));
-  }
-  return SPEIGEN_OK;
+int Solver::op_polar(Buf in, Buf out, const PanelDims& pd, bool /*have_gram*/, double* /*unused*/, int /*which_absmin*/, int warm_slot) {
+  // the fused tail kernel (tail.cu): Gram passes + q x q solve + applies in one launch, on the own rows when the panels are
+  // row-sharded; the finished rows go to every rank, and the stream waits for the peers' rows (the callers read whole panels)
+  TailSpec ts;
+  ts.producer = TAIL_PANEL; ts.T = in; ts.out = out; ts.out_all = true;
+  ts.site = (warm_slot >= 0) ? SITE_MISC : -1;
+  SPE_TRY(op_tail(ts, pd, make_stage(0.1, 0.1)));
+  return wait_latest_tail();
 }
 
 // ---- round 2: fused, row-sharded tail + MM-loop contraction ----------------------------------------
@@ -1058,6 +1054,8 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
   for (Dev& d : devs) {
     SPE_CUDA(cudaSetDevice(d.ordinal));
     SPE_CUDA(cudaMemsetAsync(d.warm, 0, 4 * kWarmStride * sizeof(double), d.st));
+    SPE_CUDA(cudaMemsetAsync(d.twarm, 0, static_cast<size_t>(N_TAIL_SITES) * 2 * kWarmDoubles * sizeof(double), d.st));
+    SPE_CUDA(cudaMemsetAsync(d.tstatus, 0, sizeof(int), d.st));
   }
   const StageConsts sc0 = make_stage(0.1, 0.1);
   int passes = 0;
@@ -1150,11 +1148,17 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
       }
       {
         Dev& d = devs[0];
-        int st = 0;
+        int st = 0, tst = 0;
         SPE_CUDA(cudaSetDevice(d.ordinal));
         SPE_CUDA(cudaMemcpyAsync(&st, d.status, sizeof(int), cudaMemcpyDeviceToHost, d.st));
+        SPE_CUDA(cudaMemcpyAsync(&tst, d.tstatus, sizeof(int), cudaMemcpyDeviceToHost, d.st));
         SPE_CUDA(cudaStreamSynchronize(d.st));
-        if (st) { rank_bad = true; break; }
+        if (tst & 4) return check_tail_status(static_cast<double>(tst));
+        if (st || tst) {          // a block that cannot be orthonormalised (zero / dependent columns): rank-deficient input
+          for (Dev& dd : devs) { cudaSetDevice(dd.ordinal); cudaMemsetAsync(dd.tstatus, 0, sizeof(int), dd.st); }
+          rank_bad = true;
+          break;
+        }
       }
     }
     if (rank_bad) {
@@ -1203,6 +1207,7 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
     for (Dev& d : devs) {           // the probe may have tripped the rank flag on a singular block; it is not an error here
       SPE_CUDA(cudaSetDevice(d.ordinal));
       SPE_CUDA(cudaMemsetAsync(d.status, 0, sizeof(int), d.st));
+      SPE_CUDA(cudaMemsetAsync(d.tstatus, 0, sizeof(int), d.st));
     }
   }
   // checks of R/spEigen.R:69,77,79 on the Ritz values that exist
