@@ -25,7 +25,8 @@ _LIB_NAME = "libspeigen_b200.so"
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    # SPEIGEN_LIB: an alternative build of the same library (kernel A/B experiments); default: the in-tree build
+    return os.environ.get("SPEIGEN_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 class SpEigenError(ValueError):

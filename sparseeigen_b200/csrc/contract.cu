@@ -113,9 +113,9 @@ constexpr int kFMT = kTJ / (8 * kFWarps);        // m-tiles per DFMA warp = 8
 // dedicated DFMA warps (one per sub-partition) that read the same swizzled A fragments: the eight DMMA warps keep a
 // pure tensor-pipe instruction stream and the DFMA warps fill the datapath whenever a DMMA warp waits on shared memory.
 template <int NTF, int RF>
-__global__ void __launch_bounds__((kConsumerWarps + (RF > 0 ? kFWarps : 0) + 1) * 32, 1)
+__global__ void __launch_bounds__((kStdWarps + (RF > 0 ? kFWarps : 0) + 1) * 32, 1)
 k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
-  constexpr int NCW = kConsumerWarps + (RF > 0 ? kFWarps : 0);   // consumer warps
+  constexpr int NCW = kStdWarps + (RF > 0 ? kFWarps : 0);   // consumer warps
   constexpr int NTD = NTF > 0 ? NTF : 1;
   constexpr int DSLOT = kMT * NTF * 2 * 256;                     // doubles of a partial slot owned by the DMMA warps
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -123,7 +123,7 @@ k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
   __shared__ __align__(8) uint64_t empty_bar[8];
   __shared__ int s_last;
   __shared__ double s_d[kMaxCols], s_rho[kMaxCols], s_wmax[kMaxCols];
-  __shared__ double s_dots[kConsumerWarps + kFWarps][kMaxCols];
+  __shared__ double s_dots[kStdWarps + kFWarps][kMaxCols];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -223,10 +223,10 @@ k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
       double s = 0.0;
       if (col < NTF * 8) {
 #pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) s += s_dots[w][col];
+        for (int w = 0; w < kStdWarps; ++w) s += s_dots[w][col];
       } else {
 #pragma unroll
-        for (int w = 0; w < kFWarps; ++w) s += s_dots[kConsumerWarps + w][col];
+        for (int w = 0; w < kFWarps; ++w) s += s_dots[kStdWarps + w][col];
       }
       prm.epi.dots[static_cast<size_t>(rt) * nout + ctid] = s;
     }
@@ -261,10 +261,10 @@ k_contract_std(const __grid_constant__ CUtensorMap tmA, const KParams prm) {
     }
   };
 
-  if (RF > 0 && warp >= kConsumerWarps) {
+  if (RF > 0 && warp >= kStdWarps) {
     // ================================ DFMA warps ================================
-    const int fw = warp - kConsumerWarps;        // 0..3, rows [64 fw, 64 fw + 64)
-    const int ftid = ctid - kConsumerWarps * 32; // 0..127
+    const int fw = warp - kStdWarps;        // 0..3, rows [64 fw, 64 fw + 64)
+    const int ftid = ctid - kStdWarps * 32; // 0..127
     double facc[kFMT][RF > 0 ? RF : 1];
 #pragma unroll
     for (int mt = 0; mt < kFMT; ++mt)
@@ -746,7 +746,7 @@ int launch_std_nt(const StreamMat& A, const KParams& prm, int grid, size_t smem,
     SPE_CUDA(cudaFuncSetAttribute(k_contract_std<NTF, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     attr_set = true;
   }
-  k_contract_std<NTF, RF><<<grid, (kConsumerWarps + (RF > 0 ? kFWarps : 0) + 1) * 32, smem, stream>>>(A.tmap, prm);
+  k_contract_std<NTF, RF><<<grid, (kStdWarps + (RF > 0 ? kFWarps : 0) + 1) * 32, smem, stream>>>(A.tmap, prm);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

@@ -67,8 +67,12 @@ struct ContractWorkspace {
 constexpr int kTJ = 256;           // output rows per CTA tile
 constexpr int kNBox = 2;           // TMA boxes (16 doubles wide) per pipeline stage
 constexpr int kTK = 16 * kNBox;    // contracted doubles per stage
-constexpr int kConsumerWarps = 8;
-constexpr int kMT = kTJ / (8 * kConsumerWarps);   // m-tiles (8 rows) per warp = 4
+constexpr int kConsumerWarps = 8;                 // transposed form: consumer warps (16 outputs each)
+#ifndef SPEIGEN_STD_WARPS
+#define SPEIGEN_STD_WARPS 8
+#endif
+constexpr int kStdWarps = SPEIGEN_STD_WARPS;      // standard form: DMMA consumer warps per CTA
+constexpr int kMT = kTJ / (8 * kStdWarps);        // m-tiles (8 rows) per warp
 constexpr int kThreads = kConsumerWarps * 32 + 32;
 constexpr int kMaxPeers = 8;
 

@@ -598,6 +598,44 @@ __global__ void k_scale_columns(double* P, const double* scale, int64_t m, int n
   P[static_cast<size_t>(r) * pitch + c] *= scale[c / e];
 }
 
+// Out[:, c] = In[:, c] for c < keep, 0 beyond (same pitch): the locked Ritz vectors of the deflated initialiser
+__global__ void k_mask_columns(const double* In, int64_t m, int ncr, int keep, int pitch, double* Out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= m * ncr) return;
+  const int64_t r = idx / ncr;
+  const int c = static_cast<int>(idx - r * ncr);
+  Out[r * pitch + c] = (c < keep) ? In[r * pitch + c] : 0.0;
+}
+// Y[:, c] = X[:, c] for c < keep
+__global__ void k_blend_columns(double* Y, const double* X, int64_t m, int keep, int pitch) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= m * keep) return;
+  const int64_t r = idx / keep;
+  const int c = static_cast<int>(idx - r * keep);
+  Y[r * pitch + c] = X[r * pitch + c];
+}
+// C = A^H B from the real cross-Gram partials of k_gram_mma (fixed-order sum), written in the "hat" form k_apply_mma consumes
+template <bool CPLX>
+__global__ void __launch_bounds__(1024) k_gram_sum_hat(const double* gram_part, int nparts, int q, double* Mh) {
+  extern __shared__ double sR[];
+  const int ncr = q * (CPLX ? 2 : 1);
+  for (int e = threadIdx.x; e < ncr * ncr; e += blockDim.x) sR[e] = sum_parts_ilp(gram_part + e, nparts, static_cast<size_t>(ncr) * ncr);
+  __syncthreads();
+  for (int e = threadIdx.x; e < q * q; e += blockDim.x) {
+    const int a = e / q, b = e - a * q;
+    if (CPLX) {
+      const double cr = sR[(2 * a) * ncr + 2 * b] + sR[(2 * a + 1) * ncr + 2 * b + 1];
+      const double ci = sR[(2 * a) * ncr + 2 * b + 1] - sR[(2 * a + 1) * ncr + 2 * b];
+      Mh[(2 * a) * ncr + 2 * b] = cr;
+      Mh[(2 * a) * ncr + 2 * b + 1] = ci;
+      Mh[(2 * a + 1) * ncr + 2 * b] = -ci;
+      Mh[(2 * a + 1) * ncr + 2 * b + 1] = cr;
+    } else {
+      Mh[a * q + b] = sR[a * ncr + b];
+    }
+  }
+}
+
 __global__ void k_take_columns(const double* In, int64_t m, int ncr_out, int pitch_in, int pitch_out, double* Out) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= m * ncr_out) return;
@@ -1222,6 +1260,28 @@ int launch_scale_columns(const PanelDims& pd, double* P, const double* scale, cu
 }
 int launch_take_columns(const PanelDims& pd_in, const double* In, const PanelDims& pd_out, double* Out, cudaStream_t st) {
   k_take_columns<<<nblk(pd_out.m * pd_out.ncr), 256, 0, st>>>(In, pd_out.m, pd_out.ncr, pd_in.pitch, pd_out.pitch, Out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_mask_columns(const PanelDims& pd, const double* In, int keep_logical, double* Out, cudaStream_t st) {
+  k_mask_columns<<<nblk(pd.m * pd.ncr), 256, 0, st>>>(In, pd.m, pd.ncr, keep_logical * (pd.cplx ? 2 : 1), pd.pitch, Out);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_blend_columns(const PanelDims& pd, double* Y, const double* X, int keep_logical, cudaStream_t st) {
+  const int keep = keep_logical * (pd.cplx ? 2 : 1);
+  if (keep <= 0) return SPEIGEN_OK;
+  k_blend_columns<<<nblk(pd.m * keep), 256, 0, st>>>(Y, X, pd.m, keep, pd.pitch);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_gram_sum_hat(const PanelDims& pd, const double* gram_part, int nparts, double* Mh, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(pd.ncr) * pd.ncr * sizeof(double);
+  if (pd.cplx) k_gram_sum_hat<true><<<1, 1024, smem, st>>>(gram_part, nparts, pd.q, Mh);
+  else k_gram_sum_hat<false><<<1, 1024, smem, st>>>(gram_part, nparts, pd.q, Mh);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

@@ -85,6 +85,11 @@ int launch_axpbypcz(const PanelDims& pd, const double* X, const double* Y, const
 int launch_scale_columns(const PanelDims& pd, double* P, const double* scale, cudaStream_t st);
 // copy the first q_out logical columns of a (wider) panel into a q_out-column panel
 int launch_take_columns(const PanelDims& pd_in, const double* In, const PanelDims& pd_out, double* Out, cudaStream_t st);
+// deflated initialiser: Out = first `keep` logical columns of In (zeros beyond); Y[:, :keep] = X[:, :keep];
+// Mh = hat(A^H B) from the cross-Gram partials of launch_gram(A, B)
+int launch_mask_columns(const PanelDims& pd, const double* In, int keep_logical, double* Out, cudaStream_t st);
+int launch_blend_columns(const PanelDims& pd, double* Y, const double* X, int keep_logical, cudaStream_t st);
+int launch_gram_sum_hat(const PanelDims& pd, const double* gram_part, int nparts, double* Mh, cudaStream_t st);
 // fixed-order sum of nparts partial panels (data mode, multi-GPU): Out = sum_r In[r]
 int launch_sum_panels(const PanelDims& pd, const double* In, int nparts, size_t part_stride, double* Out, cudaStream_t st);
 

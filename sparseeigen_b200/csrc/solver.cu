@@ -1109,42 +1109,64 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
       const double rate = (prev < 1e299) ? resid_rel / prev : 0.0;
       prev = std::min(prev, resid_rel);
       lam_low = std::min(lam_low, sv2[bq - 1]);
-      if (passes >= 3 && rate > 0.5 && bq > q) cheb_deg = std::min(cheb_deg * 2, 24);
-      int deg = cheb_deg;
+      // Locking: Ritz pairs of the leading columns that have converged (e.g. the spikes of a spiked model when q reaches into the
+      // bulk) are deflated - the filter then works on (I - X_L X_L^H) S (I - X_L X_L^H), whose wanted eigenvalues are close
+      // together, so its degree is no longer capped by the gain ratio between a spike and a bulk-edge eigenvalue.
+      int nlock = 0;
+      while (nlock < q && h_scal[64 + nlock] <= cfg.init_tol * th0) ++nlock;
+      const int deg_cap = (nlock > 0) ? 96 : 24;
+      if (passes >= 3 && rate > 0.5 && bq > q) cheb_deg = std::min(cheb_deg * 2, deg_cap);
+      int deg = std::min(cheb_deg, deg_cap);
       const double ub = sv2[bq - 1], lb = std::min(0.0, lam_low);
       const double cc = 0.5 * (ub + lb), ee = 0.5 * (ub - lb);
       auto cheb = [](int d, double x) { return x > 1.0 ? std::cosh(d * std::acosh(x)) : 1.0; };
       if (!(ub > 0.0)) deg = 1;   // the filter interval [lb, ub] assumes a PSD spectrum below the block
       if (deg > 1) {
-        const double x0 = (sv2[0] - cc) / ee, xq = (sv2[q - 1] - cc) / ee;
+        const double x0 = (sv2[nlock] - cc) / ee, xq = (sv2[q - 1] - cc) / ee;     // gain ratio among the ACTIVE wanted directions
         while (deg > 1 && !(cheb(deg, x0) <= 1e6 * cheb(deg, xq))) --deg;   // also steps down on overflow (inf/NaN)
       }
       if (deg <= 1 || !(ee > 0.0)) {
         SPE_TRY(op_polar(BV2, BQ, pdb, false, nullptr, 0, WARM_INIT));
       } else {
         Buf yprev = BV1, ycur = BT1, yspare = BV0;
-        for (Dev& d : devs) {   // Y1 = (S X - c X) / e
+        // Y <- Y - X_L (X_L^H Y): three small panel kernels per contraction when something is locked
+        auto project = [&](Buf y) -> int {
+          if (nlock == 0) return SPEIGEN_OK;
+          for (Dev& d : devs) {
+            SPE_CUDA(cudaSetDevice(d.ordinal));
+            SPE_TRY(launch_gram(pdb, d.buf[BVX], d.buf[y], d.ps.gram_part, d.st));
+            SPE_TRY(launch_gram_sum_hat(pdb, d.ps.gram_part, pdb.nblk, d.Msmall, d.st));
+            SPE_TRY(launch_apply(pdb, d.buf[BVX], d.Msmall, d.buf[BT2], nullptr, nullptr, d.ps.ticket, d.st));
+            SPE_TRY(launch_axpby(pdb, d.buf[y], d.buf[BT2], 1.0, -1.0, d.buf[y], d.st));
+          }
+          return SPEIGEN_OK;
+        };
+        for (Dev& d : devs) {   // X_L (locked Ritz vectors, zeros beyond) ; Y1 = (S X - c X) / e
           SPE_CUDA(cudaSetDevice(d.ordinal));
+          if (nlock > 0) SPE_TRY(launch_mask_columns(pdb, d.buf[BV1], nlock, d.buf[BVX], d.st));
           SPE_TRY(launch_axpby(pdb, d.buf[BV2], d.buf[BV1], 1.0 / ee, -cc / ee, d.buf[ycur], d.st));
         }
+        SPE_TRY(project(ycur));
         for (int kk = 1; kk < deg; ++kk) {   // Y_{k+1} = (2/e)(S Y_k - c Y_k) - Y_{k-1}
           SPE_TRY(op_contract(ycur, pdb, BZ, NBUF, NBUF, false, sc0));
           for (Dev& d : devs) {
             SPE_CUDA(cudaSetDevice(d.ordinal));
             SPE_TRY(launch_axpbypcz(pdb, d.buf[BZ], d.buf[ycur], d.buf[yprev], 2.0 / ee, -2.0 * cc / ee, -1.0, d.buf[yspare], d.st));
           }
+          SPE_TRY(project(yspare));
           const Buf t = yprev; yprev = ycur; ycur = yspare; yspare = t;
         }
         std::vector<double> scale(kMaxCols, 1.0);
-        for (int c = 0; c < bq; ++c) scale[c] = 1.0 / cheb(deg, (sv2[c] - cc) / ee);
+        for (int c = nlock; c < bq; ++c) scale[c] = 1.0 / cheb(deg, (sv2[c] - cc) / ee);
         for (Dev& d : devs) {
           SPE_CUDA(cudaSetDevice(d.ordinal));
           SPE_CUDA(cudaMemcpyAsync(d.rho, scale.data(), bq * sizeof(double), cudaMemcpyHostToDevice, d.st));
           SPE_TRY(launch_scale_columns(pdb, d.buf[ycur], d.rho, d.st));
+          if (nlock > 0) SPE_TRY(launch_blend_columns(pdb, d.buf[ycur], d.buf[BVX], nlock, d.st));   // keep the locked vectors in the block
         }
         SPE_TRY(sync_all());   // `scale` is a host temporary
         SPE_TRY(op_polar(ycur, BQ, pdb, false, nullptr, 0, WARM_INIT));
-        if (cfg.verbose) fprintf(stderr, "[speigen] init pass %d: Chebyshev degree %d on [%.3e, %.3e]\n", passes, deg, lb, ub);
+        if (cfg.verbose) fprintf(stderr, "[speigen] init pass %d: Chebyshev degree %d on [%.3e, %.3e], %d locked\n", passes, deg, lb, ub, nlock);
       }
       {
         Dev& d = devs[0];

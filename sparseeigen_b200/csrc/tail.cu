@@ -201,6 +201,7 @@ __device__ void exchange_gram(const TailArgs& p, const SmemPlan& sp, double* sm,
       if (tid < per && base + tid < ntri) {
         double t = piece[tid];
         for (int hh = 1; hh < H; ++hh) t += piece[hh * per + tid];
+#pragma unroll 1
         for (int r = 0; r < p.nranks; ++r) ll_store(&p.mail[r]->gram_ll[parity][p.my_rank][base + tid][0], t, tag);
       }
       __syncthreads();
@@ -213,6 +214,7 @@ __device__ void exchange_gram(const TailArgs& p, const SmemPlan& sp, double* sm,
     int i, j;
     tri_decode(tri, t, i, j);
     double s = 0.0;
+#pragma unroll 1
     for (int r = 0; r < p.nranks; ++r) {
       const unsigned long long* slot = &own->gram_ll[parity][r][t][0];
       double v = 0.0;
@@ -313,6 +315,7 @@ __device__ bool small_solve(const TailArgs& p, const SmemPlan& sp, double* sm, b
   if (lane == 0) { X[warp] = emax; X[TW + warp] = dmax; }
   __syncthreads();
   emax = 0.0; dmax = 0.0;
+#pragma unroll 1
   for (int w = 0; w < TW; ++w) { emax = fmax(emax, X[w]); dmax = fmax(dmax, X[TW + w]); }
   __syncthreads();
   const int kt4 = sp.kt4, pm = sp.pm;
@@ -334,6 +337,7 @@ __device__ bool small_solve(const TailArgs& p, const SmemPlan& sp, double* sm, b
     for (int e = tid; e < n * n; e += TT) {
       const int a = e / n, b = e - a * n;
       double s = 0.0;
+#pragma unroll 2
       for (int c = 0; c < n; ++c) s += W[a * n + c] * W[c * n + b];
       X[e] = s;
     }
@@ -341,6 +345,7 @@ __device__ bool small_solve(const TailArgs& p, const SmemPlan& sp, double* sm, b
     for (int e = tid; e < n * n; e += TT) {
       const int a = e / n, b = e - a * n;
       double s = 0.0;
+#pragma unroll 2
       for (int c = 0; c < n; ++c) s += W[a * n + c] * X[c * n + b];
       A1[e] = (a == b ? 1.0 : 0.0) - 0.5 * W[e] + 0.375 * X[e] - 0.3125 * s;
     }
@@ -360,6 +365,7 @@ __device__ bool small_solve(const TailArgs& p, const SmemPlan& sp, double* sm, b
       for (int e = tid; e < n * n; e += TT) {      // X = A W0
         const int a = e / n, b = e - a * n;
         double s = 0.0;
+#pragma unroll 2
         for (int c = 0; c < n; ++c) s += A0[a * n + c] * W[c * n + b];
         X[e] = s;
       }
@@ -368,6 +374,7 @@ __device__ bool small_solve(const TailArgs& p, const SmemPlan& sp, double* sm, b
         const int a = e / n, b = e - a * n;
         if (a <= b) {
           double s = 0.0;
+#pragma unroll 2
           for (int c = 0; c < n; ++c) s += W[c * n + a] * X[c * n + b];
           A1[a * n + b] = s;
           A1[b * n + a] = s;
@@ -474,6 +481,7 @@ __device__ bool small_solve(const TailArgs& p, const SmemPlan& sp, double* sm, b
       const int a = e / n, b = e - a * n;
       if (a <= b) {
         double s = 0.0;
+#pragma unroll 2
         for (int c = 0; c < n; ++c) s += W[a * n + c] * lam[c] * W[b * n + c];
         Mout[a * n + b] = s;
         Mout[b * n + a] = s;
@@ -514,10 +522,10 @@ __device__ void produce_rows(const TailArgs& p, int64_t r0, int64_t r1, double a
   if (p.producer == TAIL_REWEIGHT) {
     // B = d*Y - (w(|V|) - wmax) * V * rho      R/spEigen.R:170-177   (s_w[c] = column max of the weights = w(min |V[,c]|))
     const int q = p.q;
-    const int64_t nel = (r1 - r0) * q;
-    for (int64_t idx = tid; idx < nel; idx += TT) {
+    const int nel = static_cast<int>(r1 - r0) * q;          // the CTA's rows x q: far below 2^31
+    for (int idx = tid; idx < nel; idx += TT) {
       const int64_t r = r0 + idx / q;
-      const int c = static_cast<int>(idx % q);
+      const int c = idx % q;
       if (CPLX) {
         const size_t g = static_cast<size_t>(r) * pitch + 2 * c;
         const double2 v = *reinterpret_cast<const double2*>(p.in1 + g);
@@ -536,8 +544,8 @@ __device__ void produce_rows(const TailArgs& p, int64_t r0, int64_t r1, double a
     // V - 2 a R + a^2 U,  R = V1 - V, U = V2 - V1 - R      R/spEigen.R:121-127
     const int ncr = p.ncr;
     const double a2 = a * a;
-    const int64_t nel = (r1 - r0) * ncr;
-    for (int64_t idx = tid; idx < nel; idx += TT) {
+    const int nel = static_cast<int>(r1 - r0) * ncr;
+    for (int idx = tid; idx < nel; idx += TT) {
       const int64_t r = r0 + idx / ncr;
       const size_t g = static_cast<size_t>(r) * pitch + (idx % ncr);
       const double v = p.in0[g], v1 = p.in1[g], v2 = p.in2[g];
@@ -549,8 +557,15 @@ __device__ void produce_rows(const TailArgs& p, int64_t r0, int64_t r1, double a
 }
 
 // ---- Out rows = T rows * Ms (DMMA).  FINAL: stores to the destination panel(s) and accumulates the statistics.
+// g of R/spEigen.R:133-134 (one out-of-line copy: log() is ~100 instructions and the kernel is instruction-fetch bound)
+__device__ __noinline__ double penalty_g(double a, double p, double eps, double c1, double c2) {
+  return (a <= eps) ? (a * a) / (eps * c2) : log((p + a) / (p + eps)) / c1 + eps / c2;
+}
+
 // GRAM (non-final passes, NT <= 3): the Gram matrix of the product is accumulated in the same pass (output tile staged per warp
 // in shared memory, re-read as DMMA fragments) and left in the solve buffer A0 - no second trip over the rows.
+// FINAL: stores to the destination panel(s); the column statistics are taken from the same staged tile by "column owner"
+// lanes (lane c owns logical columns c and c + 32): one running minimum / sum per lane instead of per-fragment arrays.
 template <int NT, bool CPLX, bool FINAL, bool GRAM = false>
 __device__ void apply_rows(const TailArgs& p, const SmemPlan& sp, double* sm, int64_t r0, int64_t r1, double* s_stat) {
   const int n = sp.n, pm = sp.pm, pitch = p.pitch;
@@ -559,28 +574,26 @@ __device__ void apply_rows(const TailArgs& p, const SmemPlan& sp, double* sm, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 2, kk = lane & 3;
   const int64_t ntile = (r1 - r0 + 7) / 8;
-  double amin[NT][2], gs[NT][2];
+  const bool col_stats = FINAL && (p.want_absmin || p.want_gsum);
+  const bool stage = GRAM || col_stats;
+  double cmin0 = DBL_MAX, cmin1 = DBL_MAX, cgs0 = 0.0, cgs1 = 0.0;
   double sR = 0.0, sU = 0.0;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) { amin[nt][0] = amin[nt][1] = DBL_MAX; gs[nt][0] = gs[nt][1] = 0.0; }
   constexpr int NG = GRAM ? NT : 1;
   double gacc[NG][NG][2];
 #pragma unroll
   for (int i = 0; i < NG; ++i)
 #pragma unroll
     for (int j = 0; j < NG; ++j) gacc[i][j][0] = gacc[i][j][1] = 0.0;
-  double* mytile = sm + sp.u1 + static_cast<size_t>(warp) * 8 * pm;     // GRAM: per-warp staging of the 8 x ncr output tile
+  double* mytile = sm + sp.u1 + static_cast<size_t>(warp) * 8 * pm;     // per-warp staging of the 8 x ncr output tile
   const StageConsts sc = p.sc;
   // A-fragments of the next 8-row tile are fetched (L2) while the current one is multiplied
   double af[2 * NT];
   auto load_tile = [&](int64_t t, double* dst) {
     const int64_t row = r0 + t * 8 + grp;
     const bool rok = t < ntile && row < r1;
+    const double* src = p.T + row * pitch + kk;
 #pragma unroll
-    for (int k4 = 0; k4 < 2 * NT; ++k4) {
-      const int k = k4 * 4 + kk;
-      dst[k4] = (k4 < kt && rok && k < n) ? __ldcg(p.T + row * pitch + k) : 0.0;
-    }
+    for (int k4 = 0; k4 < 2 * NT; ++k4) dst[k4] = (k4 < kt && rok && k4 * 4 + kk < n) ? __ldcg(src + k4 * 4) : 0.0;
   };
   load_tile(warp, af);
   for (int64_t t = warp; t < ntile; t += TW) {
@@ -605,8 +618,13 @@ __device__ void apply_rows(const TailArgs& p, const SmemPlan& sp, double* sm, in
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int c0 = nt * 8 + 2 * kk;
-      if (!(rok && c0 < n)) continue;
+      const bool ok = rok && c0 < n;
       const bool has1 = c0 + 1 < n;
+      if (stage) {
+        mytile[grp * pm + c0] = ok ? acc[nt][0] : 0.0;
+        mytile[grp * pm + c0 + 1] = (ok && has1) ? acc[nt][1] : 0.0;
+      }
+      if (!ok) continue;
       const size_t g = static_cast<size_t>(row) * pitch + c0;
       if (!FINAL) {
         if (has1) *reinterpret_cast<double2*>(p.T + g) = make_double2(acc[nt][0], acc[nt][1]);
@@ -614,6 +632,7 @@ __device__ void apply_rows(const TailArgs& p, const SmemPlan& sp, double* sm, in
         continue;
       }
       if (p.n_out > 1) {
+#pragma unroll 1
         for (int r = 0; r < p.n_out; ++r) {
           if (has1) *reinterpret_cast<double2*>(p.out_peer[r] + g) = make_double2(acc[nt][0], acc[nt][1]);
           else p.out_peer[r][g] = acc[nt][0];
@@ -622,23 +641,6 @@ __device__ void apply_rows(const TailArgs& p, const SmemPlan& sp, double* sm, in
         double* o = p.out_peer[p.my_rank];
         if (has1) *reinterpret_cast<double2*>(o + g) = make_double2(acc[nt][0], acc[nt][1]);
         else o[g] = acc[nt][0];
-      }
-      if (p.want_absmin || p.want_gsum) {
-        if (CPLX) {
-          const double a = hypot(acc[nt][0], acc[nt][1]);
-          amin[nt][0] = fmin(amin[nt][0], a);
-          if (p.want_gsum)   // g of R/spEigen.R:133-134
-            gs[nt][0] += (a <= sc.eps) ? (a * a) / (sc.eps * sc.c2) : log((sc.p + a) / (sc.p + sc.eps)) / sc.c1 + sc.eps / sc.c2;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            if (e == 1 && !has1) continue;
-            const double a = fabs(acc[nt][e]);
-            amin[nt][e] = fmin(amin[nt][e], a);
-            if (p.want_gsum)
-              gs[nt][e] += (a <= sc.eps) ? (a * a) / (sc.eps * sc.c2) : log((sc.p + a) / (sc.p + sc.eps)) / sc.c1 + sc.eps / sc.c2;
-          }
-        }
       }
       if (p.want_squarem) {
 #pragma unroll
@@ -652,15 +654,8 @@ __device__ void apply_rows(const TailArgs& p, const SmemPlan& sp, double* sm, in
         }
       }
     }
+    if (stage) __syncwarp();
     if (GRAM) {
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int c0 = nt * 8 + 2 * kk;
-        const bool ok = rok && c0 < n;
-        mytile[grp * pm + c0] = ok ? acc[nt][0] : 0.0;
-        mytile[grp * pm + c0 + 1] = (ok && c0 + 1 < n) ? acc[nt][1] : 0.0;
-      }
-      __syncwarp();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         double f[NT];
@@ -671,32 +666,35 @@ __device__ void apply_rows(const TailArgs& p, const SmemPlan& sp, double* sm, in
 #pragma unroll
           for (int j = 0; j < NG; ++j) dmma_884(gacc[i][j][0], gacc[i][j][1], f[i], f[j]);
       }
-      __syncwarp();
     }
+    if (col_stats) {
+      const int64_t left = r1 - (r0 + t * 8);
+      const int nrow = left < 8 ? static_cast<int>(left) : 8;
+      auto own = [&](int c, double& mn, double& gsum) {
+#pragma unroll 1
+        for (int r = 0; r < nrow; ++r) {
+          const double a = CPLX ? hypot(mytile[r * pm + 2 * c], mytile[r * pm + 2 * c + 1]) : fabs(mytile[r * pm + c]);
+          mn = fmin(mn, a);
+          if (p.want_gsum) gsum += penalty_g(a, sc.p, sc.eps, sc.c1, sc.c2);
+        }
+      };
+      if (lane < p.q) own(lane, cmin0, cgs0);
+      if (lane + 32 < p.q) own(lane + 32, cmin1, cgs1);
+    }
+    if (stage) __syncwarp();
   }
   if (GRAM) {
     __syncthreads();          // every warp is done with its staging tile: the region becomes the reduction scratch
     gram_tree_store<NG>(gacc, 0, 0, n, sm + sp.a0, sm + sp.u1);
   }
   if (!FINAL) return;
-  // fixed-order reductions: rows of a warp (shuffles over grp), then warps in order
+  // fixed-order reductions: tiles of a warp in order (above), then the warps in order
+  __syncthreads();            // the staging tiles are dead: the region becomes the statistics scratch
   double* s_min = s_stat;                         // [TW][kMaxCols]
   double* s_gs = s_stat + TW * kMaxCols;          // [TW][kMaxCols]
   double* s_sq = s_gs + TW * kMaxCols;            // [TW][2]
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      double v = amin[nt][e], g = gs[nt][e];
-      v = fmin(v, __shfl_xor_sync(0xffffffffu, v, 4));
-      v = fmin(v, __shfl_xor_sync(0xffffffffu, v, 8));
-      v = fmin(v, __shfl_xor_sync(0xffffffffu, v, 16));
-      g += __shfl_xor_sync(0xffffffffu, g, 4);
-      g += __shfl_xor_sync(0xffffffffu, g, 8);
-      g += __shfl_xor_sync(0xffffffffu, g, 16);
-      const int col = nt * 8 + 2 * kk + e;
-      if (grp == 0 && col < kMaxCols) { s_min[warp * kMaxCols + col] = v; s_gs[warp * kMaxCols + col] = g; }
-    }
+  s_min[warp * kMaxCols + lane] = cmin0; s_min[warp * kMaxCols + lane + 32] = cmin1;
+  s_gs[warp * kMaxCols + lane] = cgs0;   s_gs[warp * kMaxCols + lane + 32] = cgs1;
   for (int o = 16; o; o >>= 1) {
     sR += __shfl_xor_sync(0xffffffffu, sR, o);
     sU += __shfl_xor_sync(0xffffffffu, sU, o);
@@ -705,14 +703,15 @@ __device__ void apply_rows(const TailArgs& p, const SmemPlan& sp, double* sm, in
   __syncthreads();
   double* mine = p.cta_stat + static_cast<size_t>(blockIdx.x) * kStatLen;
   if (threadIdx.x < p.q) {
-    const int col = CPLX ? 2 * threadIdx.x : threadIdx.x;
-    double v = s_min[col], g = s_gs[col];
-    for (int w = 1; w < TW; ++w) { v = fmin(v, s_min[w * kMaxCols + col]); g += s_gs[w * kMaxCols + col]; }
+    double v = s_min[threadIdx.x], g = s_gs[threadIdx.x];
+#pragma unroll 1
+    for (int w = 1; w < TW; ++w) { v = fmin(v, s_min[w * kMaxCols + threadIdx.x]); g += s_gs[w * kMaxCols + threadIdx.x]; }
     __stcg(mine + kStatAbsmin + threadIdx.x, v);
     __stcg(mine + kStatGsum + threadIdx.x, g);
   }
   if (threadIdx.x == 0) {
     double a = 0.0, b = 0.0;
+#pragma unroll 1
     for (int w = 0; w < TW; ++w) { a += s_sq[w * 2]; b += s_sq[w * 2 + 1]; }
     __stcg(mine + kStatSqR, a);
     __stcg(mine + kStatSqU, b);
@@ -754,6 +753,7 @@ __global__ void __launch_bounds__(TT, 1) k_tail(const TailArgs p) {
   if (p.producer == TAIL_REWEIGHT) {
     if (tid < p.q) {
       double v = DBL_MAX;
+#pragma unroll 1
       for (int r = 0; r < p.nranks; ++r) v = fmin(v, __ldcv(p.prev_stat + static_cast<size_t>(r) * kStatLen + kStatAbsmin + tid));
       s_w[tid] = weight_of_abs(v, p.sc);        // column max of the weights = w(min |V|)   R/spEigen.R:176
     }
@@ -764,6 +764,7 @@ __global__ void __launch_bounds__(TT, 1) k_tail(const TailArgs p) {
         a = (*p.a_cur - 1.0) / 2.0;             // :141
       } else {
         double sR = 0.0, sU = 0.0;
+#pragma unroll 1
         for (int r = 0; r < p.nranks; ++r) {
           sR += __ldcv(p.prev_stat + static_cast<size_t>(r) * kStatLen + kStatSqR);
           sU += __ldcv(p.prev_stat + static_cast<size_t>(r) * kStatLen + kStatSqU);
@@ -864,6 +865,7 @@ __global__ void __launch_bounds__(TT, 1) k_tail(const TailArgs p) {
       v = is_min ? fmin(fmin(fmin(acc[0], acc[1]), fmin(acc[2], acc[3])), fmin(fmin(acc[4], acc[5]), fmin(acc[6], acc[7])))
                  : ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     }
+#pragma unroll 1
     for (int r = 0; r < p.nranks; ++r) p.mail[r]->stat[parity][p.my_rank][tid] = v;
   }
   if (tid == 0) {
