@@ -408,8 +408,8 @@ int Solver::read_scalars(int nd) {
 // Process-wide pinned staging ring (allocated on first use, released by speigen_shutdown()): pinning memory costs ~0.3 ms per MB,
 // more than a whole small solve, so it is not re-done per call.
 struct StageRing {
-  static constexpr size_t kSlotBytes = 16u << 20;
-  static constexpr int kSlots = 24;
+  static constexpr size_t kSlotBytes = 8u << 20;
+  static constexpr int kSlots = 48;
   static constexpr int kMaxDev = 16;
   void* base = nullptr;
   cudaEvent_t ev[kSlots][kMaxDev] = {};     // an event belongs to the device whose stream records it: one per (slot, device ordinal)

@@ -76,6 +76,26 @@ def test_e2e_two_gpus_matches_one():
 
 
 @need2
+def test_e2e_two_gpus_complex_cov_and_odd_sizes():
+    """Row-sharded complex covariance (operand expansion waits for the peers' rows) and a size that does not divide evenly."""
+    Xc, _ = o.spiked_samples(611, 700, 3, 0.1, seed=5, cplx=True)
+    S = o.sample_cov(Xc)
+    a = sb.spEigen(S, 3, n_gpus=1)
+    b = sb.spEigen(S, 3, n_gpus=2)
+    n = min(len(a["info"]["F"]), len(b["info"]["F"]), 10)
+    assert np.allclose(a["info"]["F"][:n], b["info"]["F"][:n], rtol=1e-11)
+    assert np.array_equal(a["vectors"] != 0, b["vectors"] != 0)
+    assert np.all(colwise_inner(a["vectors"], b["vectors"]) > 1 - 1e-7)
+    assert np.allclose(a["values"], b["values"], rtol=1e-12)
+    Xr, _ = o.spiked_samples(1001, 250, 4, 0.05, seed=9)
+    Sr = o.sample_cov(Xr)
+    ar, br = sb.spEigen(Sr, 4, n_gpus=1), sb.spEigen(Sr, 4, n_gpus=2)
+    n = min(len(ar["info"]["F"]), len(br["info"]["F"]), 10)
+    assert np.allclose(ar["info"]["F"][:n], br["info"]["F"][:n], rtol=1e-11)
+    assert np.array_equal(ar["vectors"] != 0, br["vectors"] != 0)
+
+
+@need2
 def test_sharded_validation_scan():
     """isSymmetric.matrix / anyNA (R/spEigen.R:53,75) on a row-sharded covariance: the transposed entries live on the peer."""
     rng = np.random.default_rng(2)

@@ -1,0 +1,32 @@
+"""The reference's benchmark / quality protocols as GPU tests at reduced size: R_buildignore/package_comp_time.R:8-57
+(timing of spEigen(X, q = 3, data = TRUE), n = m/5) and R_buildignore/package_comp_param.R:50-58 (angle / pattern recovery vs rho)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+pytestmark = pytest.mark.gpu
+
+
+def test_timing_protocol_small_m():
+    import sweep_small
+    rows = sweep_small.run(ms=(100, 300), reps=5, cpu_reps=1)
+    for r in rows:
+        assert r["support_equal_oracle"] and r["min_recovery"] > 0.99
+        # the only numbers the reference publishes (running_time_data.RData, column 3): 14.0 ms at m = 100, 34.2 ms at m = 300
+        assert r["gpu_call_median_s"] < r["published_reference_s"]
+        assert r["iterations"] <= 40
+
+
+def test_recovery_protocol():
+    import recovery_vs_rho
+    lines = recovery_vs_rho.run(m=500, n=200, rhos=(0.1, 0.5, 0.9))
+    for ln in lines:
+        assert ln["support_equal_oracle"]
+        assert min(ln["angle_recovery"]) > 0.99 and min(ln["angle_recovery"]) > min(ln["standard_pca_angle"])
+        assert np.allclose(ln["pattern_recovery"], ln["oracle_pattern_recovery"])
+        assert np.allclose(ln["angle_recovery"], ln["oracle_angle_recovery"], atol=1e-6)

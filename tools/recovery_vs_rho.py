@@ -23,16 +23,11 @@ def scores(U, Vq, m):
     return angle.tolist(), pattern.tolist()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=None)
-    ap.add_argument("--m", type=int, default=500)
-    ap.add_argument("--n", type=int, default=200)
-    a = ap.parse_args()
-    m, n, q = a.m, a.n, 3
+def run(m=500, n=200, rhos=(0.1, 0.5, 0.9)):
+    q = 3
     X, Vq = synth.spiked_samples(m, n, q, 0.1, seed=42)
     lines = []
-    for rho in (0.1, 0.5, 0.9):
+    for rho in rhos:
         r = sb.spEigen(X, q, rho, data=True)
         ro = o.spEigen(X, q, rho, data=True)
         ang, pat = scores(r["vectors"], Vq, m)
@@ -41,7 +36,18 @@ def main():
                           oracle_pattern_recovery=pato, support_equal_oracle=bool(np.array_equal(r["vectors"] != 0, ro["vectors"] != 0)),
                           standard_pca_angle=np.abs(np.sum(np.conj(r["standard_vectors"]) * Vq, axis=0)).tolist(),
                           iterations=int(r["info"]["iterations"])))
-        print(json.dumps(lines[-1]), flush=True)
+    return lines
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--m", type=int, default=500)
+    ap.add_argument("--n", type=int, default=200)
+    a = ap.parse_args()
+    lines = run(a.m, a.n)
+    for ln in lines:
+        print(json.dumps(ln), flush=True)
     if a.out:
         with open(a.out, "w") as f:
             for ln in lines:

@@ -12,6 +12,19 @@ import torch            # noqa: E402
 import sparseeigen_b200 as sb    # noqa: E402
 
 
+def nvlink_kib(gpu=0):
+    """Cumulative NVLink data counters of one GPU (KiB transmitted, received), summed over its links; None if unavailable."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu)], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return None
+    tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+    rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+    return (tx, rx) if (tx or rx) else None
+
+
 def spiked_cov(m, n, q, card, dev, seed=42):
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -47,9 +60,15 @@ if __name__ == "__main__":
     for stage in (0, 5, 10):
         s.mm_steps(5, stage=stage)
         s.kernel_timing(True)
+        nv0 = nvlink_kib(0) if P > 1 else None
         ms = s.mm_steps(steps, stage=stage, timed=True)
+        nv1 = nvlink_kib(0) if P > 1 else None
         k_ms, k_n = s.kernel_time()
         d = s.tail_diag()
+        if nv0 and nv1:
+            # per MM update on GPU 0 (the counters also see the stats-only tail + final copy of mm_steps: < 1 step's worth)
+            print(f"NVLink GPU0 per MM update: tx {(nv1[0] - nv0[0]) * 1.024 / steps:.0f} kB, rx {(nv1[1] - nv0[1]) * 1.024 / steps:.0f} kB; "
+                  f"algorithmic: rows to {P - 1} peers = {(P - 1) * (-(-m // P)) * q * 8 / 1e3:.0f} kB + mailbox words", flush=True)
         print(f"m={m} q={q} stage={stage}: {1e3 * ms / steps:.1f} us per MM update, K1 {1e3 * k_ms / max(k_n, 1):.1f} us, "
               f"rest {1e3 * (ms - k_ms) / steps:.1f} us; tail passes {d["passes"]} sweeps {d["sweeps"]} clock_us {d["clock_us"]} jacobi {d["jacobi_us"]}", flush=True)
     s.init()
