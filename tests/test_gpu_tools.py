@@ -29,4 +29,6 @@ def test_recovery_protocol():
         assert ln["support_equal_oracle"]
         assert min(ln["angle_recovery"]) > 0.99 and min(ln["angle_recovery"]) > min(ln["standard_pca_angle"])
         assert np.allclose(ln["pattern_recovery"], ln["oracle_pattern_recovery"])
-        assert np.allclose(ln["angle_recovery"], ln["oracle_angle_recovery"], atol=1e-6)
+        # the last continuation stage stops on a 1e-9 relative change of the objective, i.e. with iterates converged to ~1e-4;
+        # when the stop rule fires one iteration apart in the two implementations the angles differ at that level
+        assert np.allclose(ln["angle_recovery"], ln["oracle_angle_recovery"], atol=2e-4)
