@@ -22,7 +22,10 @@ def nvlink_kib(gpu=0):
         return None
     tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
     rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
-    return (tx, rx) if (tx or rx) else None
+    if not (tx or rx):
+        print("nvidia-smi nvlink -gt d gave no counters:", out[:300].replace("\n", " | "), flush=True)
+        return None
+    return (tx, rx)
 
 
 def spiked_cov(m, n, q, card, dev, seed=42):
