@@ -4,6 +4,7 @@
 #include "../../include/speigen_b200.h"
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 namespace speigen {
 namespace {
@@ -935,8 +936,16 @@ int launch_tail_nt(const TailArgs& a, int grid, cudaStream_t st) {
   const SmemPlan sp = plan_smem(a.ncr, NT);
   TailArgs args = a;
   void* params[] = {&args};
-  const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_tail<NT, CPLX>), dim3(grid), dim3(TT), params,
-                                                    sp.total, st);
+  // Cooperative launch = the driver guarantees that all CTAs are co-resident (the kernel waits inside).  SPEIGEN_TAIL_COOP=0
+  // (measurement only) uses a plain launch, which is co-resident in practice on an otherwise idle GPU (grid <= #SMs, 1 CTA/SM).
+  static const bool coop = []() { const char* v = getenv("SPEIGEN_TAIL_COOP"); return !(v && v[0] == '0'); }();
+  cudaError_t e;
+  if (coop) {
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_tail<NT, CPLX>), dim3(grid), dim3(TT), params, sp.total, st);
+  } else {
+    k_tail<NT, CPLX><<<grid, TT, sp.total, st>>>(args);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) {
     set_error("tail kernel launch failed: %s (grid %d, %zu bytes of shared memory)", cudaGetErrorString(e), grid, sp.total);
     return SPEIGEN_ERR_CUDA;
