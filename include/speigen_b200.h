@@ -39,7 +39,8 @@ extern "C" {
                                          svd() would return an arbitrary completion; this library refuses instead of returning it */
 #define SPEIGEN_ERR_NOT_CONVERGED 27  /* the block subspace iteration that replaces eigen()/svd() (R/spEigen.R:68,76) did not reach
                                          init_tol within init_max_passes */
-#define SPEIGEN_ERR_TIMEOUT 28        /* a GPU waited longer than exchange_timeout_ms for a peer in the fused exchange */
+#define SPEIGEN_ERR_TIMEOUT 28        /* a GPU waited longer than exchange_timeout_ms for a peer in the fused exchange; the ranks'
+                                         exchange epochs are no longer aligned: destroy the solver (the one-shot calls do) */
 
 /* ---- configuration: the constants the reference hard-codes, plus device options ---------------- */
 typedef struct speigen_cfg {

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 
@@ -498,6 +499,8 @@ int Solver::load_host(const double* X) {
     return SPEIGEN_OK;
   }
   // ---- staged upload: worker threads each take whole chunks (copy into a pinned slot, enqueue the DMA, move on)
+  static std::mutex ring_mutex;                 // one staged upload at a time per process (the ring is process-wide)
+  std::lock_guard<std::mutex> ring_lock(ring_mutex);
   StageRing& ring = stage_ring_global();
   SPE_CUDA(cudaSetDevice(devs[0].ordinal));
   SPE_TRY(ring.ensure());
