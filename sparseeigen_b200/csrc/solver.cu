@@ -1082,8 +1082,18 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
     int cheb_deg = 1;
     double lam_low = 0.0;
     sv2.assign(bq, 0.0);
+    // Rayleigh-Ritz (cross-Gram, q x q eigen-solve, two applies, residual norms, one host read-back) is only needed to TEST
+    // convergence and to steer the filter; a plain pass is Q <- polar(S Q) - one contraction and one tail kernel, no read-back.
+    // With a measured geometric rate the next test is scheduled for the pass that is predicted to reach init_tol.
+    int rr_skip = 0, last_rr_pass = 0;
+    double last_rr_resid = 0.0;
     for (passes = 1; passes <= cfg.init_max_passes; ++passes) {
       SPE_TRY(op_contract(BQ, pdb, BZ, NBUF, NBUF, false, sc0));
+      if (rr_skip > 0 && passes < cfg.init_max_passes) {
+        --rr_skip;
+        SPE_TRY(op_polar(BZ, BQ, pdb, false, nullptr, 0, WARM_INIT));
+        continue;
+      }
       for (Dev& d : devs) {
         SPE_CUDA(cudaSetDevice(d.ordinal));
         SPE_TRY(launch_gram(pdb, d.buf[BQ], d.buf[BZ], d.ps.gram_part, d.st));
@@ -1109,9 +1119,21 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
       // Ritz vectors X are filtered with T_deg((S - c)/e), [c - e, c + e] = [lower bound, smallest Ritz value of the
       // block] (the unwanted interval), each column rescaled by 1 / T_deg(x_c) so the block stays well conditioned.
       // The degree doubles while convergence stays slow, capped so that wanted directions differ by <= 1e6 in gain.
-      const double rate = (prev < 1e299) ? resid_rel / prev : 0.0;
+      // per-pass rate since the previous Rayleigh-Ritz test
+      double rate = 0.0;
+      if (last_rr_pass > 0 && last_rr_resid > 0.0) rate = std::pow(resid_rel / last_rr_resid, 1.0 / static_cast<double>(passes - last_rr_pass));
+      last_rr_pass = passes;
+      last_rr_resid = resid_rel;
       prev = std::min(prev, resid_rel);
       lam_low = std::min(lam_low, sv2[bq - 1]);
+      if (cheb_deg == 1 && rate > 0.0 && rate < 0.5 && resid_rel > cfg.init_tol) {
+        const double need = std::ceil(std::log(cfg.init_tol / resid_rel) / std::log(rate));     // passes predicted to reach the tolerance
+        // test one pass AFTER the predicted one: the MM trajectory is sensitive to the start vectors at the 1e-15 level (its
+        // late SQUAREM steps amplify by |a| ~ 1e3..1e5), so the initialiser should end below init_tol, not at it
+        // (where a pass is cheap, i.e. the matrix is small; on a 20 GB matrix a pass costs ten tests and every test is made)
+        const bool cheap_pass = static_cast<double>(devs[0].a_rows) * static_cast<double>(devs[0].a_ld) * sizeof(double) < 256e6;
+        rr_skip = static_cast<int>(std::min(6.0, std::max(0.0, cheap_pass ? need : need - 1.0)));
+      }
       // Locking: Ritz pairs of the leading columns that have converged (e.g. the spikes of a spiked model when q reaches into the
       // bulk) are deflated - the filter then works on (I - X_L X_L^H) S (I - X_L X_L^H), whose wanted eigenvalues are close
       // together, so its degree is no longer capped by the gain ratio between a spike and a bulk-edge eigenvalue.
