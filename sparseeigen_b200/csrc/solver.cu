@@ -1130,9 +1130,9 @@ int Solver::init_vectors(const double* V0_host, speigen_out* out) {
         const double need = std::ceil(std::log(cfg.init_tol / resid_rel) / std::log(rate));     // passes predicted to reach the tolerance
         // test one pass AFTER the predicted one: the MM trajectory is sensitive to the start vectors at the 1e-15 level (its
         // late SQUAREM steps amplify by |a| ~ 1e3..1e5), so the initialiser should end below init_tol, not at it
-        // Only where a pass is cheap (small matrix): on a 20 GB shard a pass costs ten tests, a mispredicted pass would cost more
-        // than all the skipped tests save, so every pass is tested there.
-        const bool cheap_pass = static_cast<double>(devs[0].a_rows) * static_cast<double>(devs[0].a_ld) * sizeof(double) < 256e6;
+        // Only where a pass is cheap (a shard below 4 GB streams in < 0.7 ms, about one test): on a 20 GB shard a pass costs
+        // ten tests, a mispredicted pass would cost more than all the skipped tests save, so every pass is tested there.
+        const bool cheap_pass = static_cast<double>(devs[0].a_rows) * static_cast<double>(devs[0].a_ld) * sizeof(double) < 4e9;
         rr_skip = cheap_pass ? static_cast<int>(std::min(6.0, std::max(0.0, need))) : 0;
       }
       // Locking: Ritz pairs of the leading columns that have converged (e.g. the spikes of a spiked model when q reaches into the
