@@ -196,6 +196,8 @@ int speigen_solver_sync(speigen_solver* s);
  * sweeps, [7] number of clock stamps, [8..] phase clock of CTA 0 in ns since kernel entry (produce, then per pass: Gram, exchange,
  * solve, apply).  Measurement side channel only. */
 int speigen_solver_tail_diag(speigen_solver* s, double* out48);
+/* Test hook: a device-side wait for an exchange epoch that never comes, bounded by budget_ms -> SPEIGEN_ERR_TIMEOUT (28). */
+int speigen_solver_selftest_timeout(speigen_solver* s, int32_t budget_ms);
 /* 0: single GPU (no exchange), 1: NCCL collectives, 2: fused peer-store exchange (valid after speigen_solver_init_comm) */
 int speigen_solver_exchange_mode(speigen_solver* s);
 /* CUDA-event timing of the contraction kernel launches of local device 0 (for the roofline line of bench.py). */

@@ -139,6 +139,7 @@ def lib():
     L.speigen_solver_mm_steps.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, _dp, C.POINTER(C.c_float)]
     L.speigen_solver_sync.argtypes = [C.c_void_p]
     L.speigen_solver_tail_diag.argtypes = [C.c_void_p, _dp]
+    L.speigen_solver_selftest_timeout.argtypes = [C.c_void_p, C.c_int32]
     L.speigen_solver_exchange_mode.argtypes = [C.c_void_p]
     L.speigen_solver_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
     L.speigen_solver_kernel_time.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int32)]

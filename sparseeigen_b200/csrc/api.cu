@@ -347,6 +347,18 @@ int speigen_solver_mm_steps(speigen_solver* s, int32_t nsteps, int32_t stage, do
   DeviceRestore restore_device__;
   return s->impl.mm_steps(nsteps, stage, rho, d, ms_out);
 }
+// Test hook for the bounded device-side waits: waits on the own mailbox for an exchange epoch that no peer will ever publish,
+// with the given budget, and returns what a solve would return in that situation (SPEIGEN_ERR_TIMEOUT).
+int speigen_solver_selftest_timeout(speigen_solver* s, int32_t budget_ms) {
+  DeviceRestore restore_device__;
+  if (!s) return SPEIGEN_ERR_ARG;
+  Solver& S = s->impl;
+  Dev& d = S.devs[0];
+  cudaSetDevice(d.ordinal);
+  API_TRY(launch_wait_flags(d.mail->stat_flag, kFlagStride, 1, S.stat_epoch + 1000000ull, d.tstatus,
+                            static_cast<long long>(budget_ms) * 1000000ll, d.st));
+  return tail_status(S);
+}
 int speigen_solver_tail_diag(speigen_solver* s, double* out48) {
   DeviceRestore restore_device__;
   if (!s || !out48) return SPEIGEN_ERR_ARG;

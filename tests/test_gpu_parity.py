@@ -481,6 +481,23 @@ def test_unconverged_initialiser_is_an_error():
     assert not r["info"]["init_converged"] and r["vectors"].shape == (600, 4)
 
 
+def test_device_side_waits_are_bounded():
+    """A peer that never publishes its exchange epoch (a rank that failed or left early) must not hang the GPU: the wait gives
+    up after the budget, the call returns SPEIGEN_ERR_TIMEOUT and the solver object can still be destroyed / the library reused."""
+    import time
+    X, _ = o.spiked_samples(300, 90, 3, 0.1, seed=5)
+    S = o.sample_cov(X)
+    with sb.Solver(300, 3) as s:
+        s.load(S)
+        t0 = time.perf_counter()
+        rc = s.L.speigen_solver_selftest_timeout(s.h, 200)
+        dt = time.perf_counter() - t0
+        assert rc == 28 and 0.15 < dt < 5.0, (rc, dt)
+        assert b"waited more than" in s.L.speigen_last_error()
+    r = sb.spEigen(S, 3)
+    assert r["vectors"].shape == (300, 3)
+
+
 def test_max_iter_ends_a_stage_not_the_schedule():
     """R/spEigen.R:151: k >= max_iter only breaks the inner loop; the remaining (p, eps) stages still run two iterations each."""
     X, _ = o.spiked_samples(400, 100, 3, 0.1, seed=12)
