@@ -470,9 +470,14 @@ def main():
             sb.spEigen(np.asfortranarray(S_host[::25, ::25]), q, n_gpus=world)
             dt, r = e2e_calls(sb, S_host, q, world, calls)
             upd = 2 * r["info"]["iterations"]
+            h2d = int(sb.lib().speigen_last_upload_bytes())       # counted by the library from the copies it issued
             line["e2e"] = {"value": upd / dt, "unit": UNIT,
-                           "h2d_bytes_per_step": int(8 * m * m / upd), "d2h_bytes_per_step": int((2 * 8 * m * q + 8 * q) / upd),
-                           "h2d_bytes_per_call": int(8 * m * m), "d2h_bytes_per_call": int(2 * 8 * m * q + 8 * q),
+                           "h2d_bytes_per_step": int(h2d / upd), "d2h_bytes_per_step": int((2 * 8 * m * q + 8 * q) / upd),
+                           "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": int(2 * 8 * m * q + 8 * q),
+                           "host_bytes_read_per_call": int(8 * m * m),
+                           "upload": ("Hermitian-half: one tile of every transposed 2048 x 2048 pair crosses PCIe, isSymmetric/anyNA "
+                                      "are evaluated by the host workers against the tile that stays, the device rebuilds it"
+                                      if r["info"]["upload_half"] else "full matrix"),
                            "calls": calls, "seconds_per_call": dt, "n_gpus": world, "host_memory": "pageable",
                            "mm_updates_counted_per_call": upd,
                            "counting": "2 MM updates (V1, V2) per outer iteration of R/spEigen.R:119-120; the call also runs "

@@ -101,7 +101,9 @@ typedef struct speigen_out {
   double seconds_loop;
   double seconds_setup;        /* one-shot calls: device allocation, peer mappings (0 when a cached context was reused) */
   double seconds_prepare;      /* validation scan / centring (R/spEigen.R:53,60,75) */
-  int32_t upload_staged;       /* 1: the host matrix was pageable and went through the pinned staging ring */
+  int32_t upload_staged;       /* bit 0: the host matrix was pageable and went through the pinned staging ring;
+                                  bit 1: Hermitian-half upload (one tile of every transposed pair crossed PCIe, isSymmetric
+                                  evaluated on the host, the other tile rebuilt on the device) */
   int32_t polar_passes_max;    /* largest number of Gram passes any polar factor of the MM loop needed (2 = the usual case) */
 } speigen_out;
 
@@ -196,6 +198,16 @@ int speigen_solver_sync(speigen_solver* s);
  * sweeps, [7] number of clock stamps, [8..] phase clock of CTA 0 in ns since kernel entry (produce, then per pass: Gram, exchange,
  * solve, apply).  Measurement side channel only. */
 int speigen_solver_tail_diag(speigen_solver* s, double* out48);
+/* Hermitian-half upload of a covariance matrix (R/spEigen.R:75 guarantees S = S^H): how the last load moved the data. */
+int speigen_solver_upload_info(speigen_solver* s, int32_t* staged, int32_t* half, int32_t* host_verified);
+/* Host-only test hooks of that upload (no GPU): the complete procedure - unit plan, staging, isSymmetric's sums
+ * sum|S - S^H| and sum|S| (R/spEigen.R:75), transposed rebuild - emulated in host memory.  S, A_out: m x m column-major
+ * (interleaved complex), A_out must not alias S. */
+int speigen_host_half_upload_emulate(const double* S, int64_t m, int32_t is_complex, int32_t world, int64_t block,
+                                     int64_t slot_bytes, int32_t use_simd, double* A_out, double* diff, double* sabs);
+int speigen_host_has_avx2(void);
+/* Bytes the most recent host-matrix load of this process (resident or one-shot) moved host -> device. */
+int64_t speigen_last_upload_bytes(void);
 /* Test hook: a device-side wait for an exchange epoch that never comes, bounded by budget_ms -> SPEIGEN_ERR_TIMEOUT (28). */
 int speigen_solver_selftest_timeout(speigen_solver* s, int32_t budget_ms);
 /* 0: single GPU (no exchange), 1: NCCL collectives, 2: fused peer-store exchange (valid after speigen_solver_init_comm) */

@@ -140,6 +140,12 @@ def lib():
     L.speigen_solver_sync.argtypes = [C.c_void_p]
     L.speigen_solver_tail_diag.argtypes = [C.c_void_p, _dp]
     L.speigen_solver_selftest_timeout.argtypes = [C.c_void_p, C.c_int32]
+    L.speigen_solver_upload_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3
+    L.speigen_host_half_upload_emulate.argtypes = [_dp, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32,
+                                                   _dp, _dp, _dp]
+    L.speigen_host_has_avx2.argtypes = []
+    L.speigen_last_upload_bytes.argtypes = []
+    L.speigen_last_upload_bytes.restype = C.c_int64
     L.speigen_solver_exchange_mode.argtypes = [C.c_void_p]
     L.speigen_solver_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
     L.speigen_solver_kernel_time.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int32)]
@@ -269,7 +275,7 @@ class _OutBuffers:
                     init_passes=self.c.init_passes, init_converged=bool(self.c.init_converged),
                     init_residual=self.c.init_residual, seconds_upload=self.c.seconds_upload,
                     seconds_init=self.c.seconds_init, seconds_loop=self.c.seconds_loop, seconds_setup=self.c.seconds_setup,
-                    seconds_prepare=self.c.seconds_prepare, upload_staged=bool(self.c.upload_staged),
+                    seconds_prepare=self.c.seconds_prepare, upload_staged=bool(self.c.upload_staged & 1), upload_half=bool(self.c.upload_staged & 2),
                     polar_passes_max=self.c.polar_passes_max,
                     F=self.F[:k].copy(), step_a=self.step_a[:k].copy(), backtracks_per_k=self.bt[:k].copy(),
                     stage_of_k=self.stage[:k].copy())

@@ -1,5 +1,6 @@
 // extern "C" surface of libspeigen_b200.so (declared in include/speigen_b200.h).
 #include "solver.cuh"
+#include "host_pack.h"
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -177,6 +178,7 @@ int speigen_solver_shard_buffer(speigen_solver* s, int32_t li, double** dev_ptr,
   if (lo) *lo = d.lo;
   if (hi) *hi = d.hi;
   s->impl.loaded = true;
+  s->impl.host_verified = false;
   return SPEIGEN_OK;
 }
 int speigen_solver_prepare(speigen_solver* s) {
@@ -359,6 +361,22 @@ int speigen_solver_selftest_timeout(speigen_solver* s, int32_t budget_ms) {
                             static_cast<long long>(budget_ms) * 1000000ll, d.st));
   return tail_status(S);
 }
+// Host-only test hooks of the Hermitian-half upload (host_pack.h): no GPU needed.
+int speigen_host_half_upload_emulate(const double* S, int64_t m, int32_t is_complex, int32_t world, int64_t block,
+                                     int64_t slot_bytes, int32_t use_simd, double* A_out, double* diff, double* sabs) {
+  if (!S || !A_out || !diff || !sabs || m < 1 || world < 1 || block < 1 || slot_bytes < 16) return SPEIGEN_ERR_ARG;
+  emulate_half_upload(S, m, is_complex ? 2 : 1, world, block, static_cast<size_t>(slot_bytes), use_simd, A_out, diff, sabs);
+  return SPEIGEN_OK;
+}
+int speigen_host_has_avx2(void) { return host_has_avx2() ? 1 : 0; }
+int64_t speigen_last_upload_bytes(void) { return static_cast<int64_t>(last_upload_bytes()); }
+int speigen_solver_upload_info(speigen_solver* s, int32_t* staged, int32_t* half, int32_t* host_verified) {
+  if (!s) return SPEIGEN_ERR_ARG;
+  if (staged) *staged = s->impl.upload_staged ? 1 : 0;
+  if (half) *half = s->impl.upload_half ? 1 : 0;
+  if (host_verified) *host_verified = s->impl.host_verified ? 1 : 0;
+  return SPEIGEN_OK;
+}
 int speigen_solver_tail_diag(speigen_solver* s, double* out48) {
   DeviceRestore restore_device__;
   if (!s || !out48) return SPEIGEN_ERR_ARG;
@@ -437,7 +455,7 @@ static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data,
   if (rc == SPEIGEN_OK) rc = s->impl.load_host(X);
   const double t1 = wall_s();
   out->seconds_upload = t1 - t0;
-  out->upload_staged = s->impl.upload_staged ? 1 : 0;
+  out->upload_staged = (s->impl.upload_staged ? 1 : 0) | (s->impl.upload_half ? 2 : 0);
   if (rc == SPEIGEN_OK) rc = s->impl.prepare();
   out->seconds_prepare = wall_s() - t1;
   if (rc == SPEIGEN_OK) rc = s->impl.init_vectors(V0, out);

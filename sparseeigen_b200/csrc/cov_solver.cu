@@ -1008,6 +1008,7 @@ static int load_cov_of_data_impl(Solver& S, const double* X_src, int64_t n, int6
     if (rc != SPEIGEN_OK) return rc;
   }
   S.loaded = true;
+  S.host_verified = false;
   return SPEIGEN_OK;
 }
 

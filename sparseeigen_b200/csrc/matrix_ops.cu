@@ -1,4 +1,5 @@
 #include "matrix_ops.cuh"
+#include "host_pack.h"
 #include "../../include/speigen_b200.h"
 #include <cfloat>
 
@@ -94,6 +95,43 @@ __global__ void __launch_bounds__(256) k_scan_cov(const double* A, int64_t rows,
   }
 }
 
+// Second half of the Hermitian-half upload (host_pack.h): every element whose super-tile did not cross PCIe is rebuilt as the
+// conjugate of its transposed partner, which did - read from the shard that owns it (own matrix on one GPU, a peer's over
+// NVLink when S is row-sharded inside one process).  Same 32 x 32 staging as the scan above; uploaded elements are never
+// written and non-uploaded ones never read, so the kernels of different GPUs may run concurrently.
+template <int E>
+__global__ void __launch_bounds__(256) k_mirror_cov(double* A, int64_t rows, int64_t m, int64_t ld, int64_t lo, int64_t block,
+                                                    const ScanPeers peers) {
+  __shared__ double tileT[32][32 * E + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t tr = (rows + 31) / 32, tc = (m + 31) / 32;
+  const int64_t ntiles = tr * tc;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t tj = t / tc, ti = t - tj * tc;
+    // a 32 x 32 tile meets at most 2 x 2 super-tiles: its corners tell whether anything in it has to be rebuilt
+    const int64_t rf = lo + tj * 32, rl = lo + min(tj * 32 + 31, rows - 1), cf = ti * 32, cl = min(ti * 32 + 31, m - 1);
+    const bool need = !half_tile_uploaded(rf, cf, block) || !half_tile_uploaded(rf, cl, block) ||
+                      !half_tile_uploaded(rl, cf, block) || !half_tile_uploaded(rl, cl, block);
+    if (!need) continue;
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t gg = ti * 32 + r, jl = tj * 32 + tx, ii = lo + jl;      // source element (gg, ii) = partner of (ii, gg)
+      const bool ok = gg < m && jl < rows && !half_tile_uploaded(ii, gg, block);
+      const double* src = ok ? peers.A[gg / peers.rps] + (gg % peers.rps) * ld + ii * E : nullptr;
+#pragma unroll
+      for (int e = 0; e < E; ++e) tileT[r][tx * E + e] = ok ? src[e] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t j = tj * 32 + r, i = ti * 32 + tx;
+      if (j < rows && i < m && !half_tile_uploaded(lo + j, i, block)) {
+        A[j * ld + i * E] = tileT[tx][r * E];
+        if (E == 2) A[j * ld + i * E + 1] = -tileT[tx][r * E + E - 1];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <int E>
 __global__ void __launch_bounds__(256) k_row_sums(const double* A, int64_t nloc, int64_t ld, double* sums) {
   __shared__ double s_red[E][8];
@@ -170,6 +208,18 @@ int launch_scan_cov(const double* A, int64_t rows, int64_t m, int64_t ld, int64_
   peers.rps = (shard_ptrs && nshards > 1) ? rows_per_shard : (m > 0 ? m : 1);
   if (cplx) k_scan_cov<2><<<kScanBlocks, 256, 0, st>>>(A, rows, m, ld, lo, full_check, peers, part, ticket, out4);
   else k_scan_cov<1><<<kScanBlocks, 256, 0, st>>>(A, rows, m, ld, lo, full_check, peers, part, ticket, out4);
+  SPE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return SPEIGEN_OK;
+}
+int launch_mirror_cov(double* A, int64_t rows, int64_t m, int64_t ld, int64_t lo, int cplx, int64_t block,
+                      const double* const* shard_ptrs, int nshards, int64_t rows_per_shard, cudaStream_t st) {
+  if (rows <= 0) return SPEIGEN_OK;
+  ScanPeers peers{};
+  for (int i = 0; i < 8; ++i) peers.A[i] = (shard_ptrs && i < nshards) ? shard_ptrs[i] : A;
+  peers.rps = (shard_ptrs && nshards > 1) ? rows_per_shard : (m > 0 ? m : 1);
+  if (cplx) k_mirror_cov<2><<<kScanBlocks, 256, 0, st>>>(A, rows, m, ld, lo, block, peers);
+  else k_mirror_cov<1><<<kScanBlocks, 256, 0, st>>>(A, rows, m, ld, lo, block, peers);
   SPE_CUDA(cudaGetLastError());
   note_launch(1);
   return SPEIGEN_OK;

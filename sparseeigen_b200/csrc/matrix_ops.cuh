@@ -14,6 +14,10 @@ constexpr int kScanBlocks = 148 * 4;
 int launch_scan_cov(const double* A, int64_t rows, int64_t m, int64_t ld, int64_t lo, int cplx, int full_check,
                     const double* const* shard_ptrs, int nshards, int64_t rows_per_shard, double* part, int* ticket,
                     double* out4, cudaStream_t st);
+// Hermitian-half upload, device side: rebuild every element whose super-tile (edge `block`, host_pack.h) was not uploaded as the
+// conjugate of its transposed partner (shard_ptrs as in launch_scan_cov).
+int launch_mirror_cov(double* A, int64_t rows, int64_t m, int64_t ld, int64_t lo, int cplx, int64_t block,
+                      const double* const* shard_ptrs, int nshards, int64_t rows_per_shard, cudaStream_t st);
 // Data shard (rows = variables, contiguous = local samples).  sums[j*(1+cplx)+e] = sum_i A[j][i]
 int launch_row_sums(const double* A, int64_t rows, int64_t nloc, int64_t ld, int cplx, double* sums, cudaStream_t st);
 // A[j][i] -= mean[j] ; sq[j] = sum_i |A[j][i]|^2   (mean = sums / n_total)

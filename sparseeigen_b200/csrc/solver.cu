@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include "host_pack.h"
 #include <mutex>
 #include <string>
 #include <thread>
@@ -249,6 +250,7 @@ void Solver::destroy() {
 
 void Solver::reset_for_reuse() {
   loaded = prepared = inited = false;
+  host_verified = upload_half = false;
   scale_max = 0.0;
   sv2.clear();
   contractions = 0;
@@ -452,8 +454,147 @@ struct UploadChunk {
 
 }  // namespace
 
+// Hermitian-half upload (host_pack.h): applies to a covariance matrix driven by one process whose GPUs can read each other's
+// shards.  SPEIGEN_HALF_UPLOAD=0 disables it; SPEIGEN_HALF_BLOCK / SPEIGEN_HALF_MIN_BYTES override the super-tile edge and the
+// size threshold (tests run it on small matrices that way).
+static int64_t env_i64(const char* name, int64_t dflt) {
+  const char* v = getenv(name);
+  if (!v || !v[0]) return dflt;
+  const long long x = atoll(v);
+  return x > 0 ? static_cast<int64_t>(x) : dflt;
+}
+
+static std::atomic<long long> g_last_upload_bytes{0};
+long long last_upload_bytes() { return g_last_upload_bytes.load(); }
+
+int Solver::load_host_half(const double* X, bool pageable) {
+  const int e = 1 + cplx;
+  const int64_t block = env_i64("SPEIGEN_HALF_BLOCK", kHalfBlock);
+  const size_t slot_bytes = StageRing::kSlotBytes;
+  std::vector<std::pair<int64_t, int64_t>> ranges;
+  for (Dev& d : devs) ranges.emplace_back(d.lo, d.hi);
+  const std::vector<HalfUnit> units = plan_half_upload(m, e, ranges, block, slot_bytes);
+  const bool compare = cfg.check_symmetric || cfg.check_na;
+  upload_staged = pageable;
+  {
+    long long bytes = 0;
+    for (const HalfUnit& u : units) bytes += static_cast<long long>(u.nr) * u.nc * e * static_cast<long long>(sizeof(double));
+    g_last_upload_bytes.store(bytes);
+  }
+  static std::mutex ring_mutex;
+  std::unique_lock<std::mutex> ring_lock(ring_mutex, std::defer_lock);
+  StageRing& ring = stage_ring_global();
+  if (pageable) {
+    ring_lock.lock();
+    SPE_CUDA(cudaSetDevice(devs[0].ordinal));
+    SPE_TRY(ring.ensure());
+  }
+  const int hw = static_cast<int>(std::thread::hardware_concurrency());
+  const int nthreads = std::max(1, std::min<int>(StageRing::kSlots / 2, hw > 0 ? hw : 1));
+  std::atomic<size_t> next{0};
+  std::atomic<int> failed{0};
+  std::vector<int> dev_ord(devs.size());
+  std::vector<cudaStream_t> dev_st(devs.size());
+  for (size_t i = 0; i < devs.size(); ++i) { dev_ord[i] = devs[i].ordinal; dev_st[i] = devs[i].st; }
+  std::vector<double> unit_diff(units.size(), 0.0), unit_sabs(units.size(), 0.0);   // summed in unit order: deterministic
+  const size_t spitch = static_cast<size_t>(m) * e * sizeof(double);
+  auto worker = [&](int w) {
+    int use = 0;
+    const int my_slots = (StageRing::kSlots - w + nthreads - 1) / nthreads;
+    std::vector<int> slot_dev(my_slots, -1);
+    std::vector<double> scratch(2 * 128 * 128);
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= units.size() || failed.load()) break;
+      const HalfUnit& u = units[i];
+      Dev& d = devs[u.dev];
+      const double* src = X + (static_cast<size_t>(u.r0) * m + u.c0) * e;           // A row r = column r of S (contiguous)
+      const double* partner = X + (static_cast<size_t>(u.c0) * m + u.r0) * e;
+      char* dst = reinterpret_cast<char*>(d.A + (u.r0 - d.lo) * d.a_ld + u.c0 * e);
+      const size_t dpitch = static_cast<size_t>(d.a_ld) * sizeof(double);
+      const size_t width = static_cast<size_t>(u.nc) * e * sizeof(double);
+      const size_t lds = static_cast<size_t>(m) * e;
+      double acc[3] = {0.0, 0.0, 0.0};
+      cudaError_t err = cudaSuccess;
+      if (pageable) {
+        const int k = use % my_slots;
+        const int slot = w + k * nthreads;
+        ++use;
+        if (slot_dev[k] >= 0) {
+          cudaEvent_t pe = nullptr;
+          if (cudaSetDevice(dev_ord[slot_dev[k]]) != cudaSuccess || ring.event(slot, dev_ord[slot_dev[k]], &pe) != cudaSuccess ||
+              cudaEventSynchronize(pe) != cudaSuccess) { failed.store(1); break; }
+        }
+        char* stage = static_cast<char*>(ring.base) + static_cast<size_t>(slot) * slot_bytes;
+        // one pass over the unit: every 128 x 128 sub-tile is streamed into the slot and compared with its partner while in cache
+        half_unit_pack_and_sums(src, lds, partner, lds, u.nr, u.nc, e, reinterpret_cast<double*>(stage), compare, scratch.data(), acc);
+        err = cudaSetDevice(dev_ord[u.dev]);
+        if (err == cudaSuccess)
+          err = cudaMemcpy2DAsync(dst, dpitch, stage, width, width, static_cast<size_t>(u.nr), cudaMemcpyHostToDevice, dev_st[u.dev]);
+        cudaEvent_t me = nullptr;
+        if (err == cudaSuccess) err = ring.event(slot, dev_ord[u.dev], &me);
+        if (err == cudaSuccess) err = cudaEventRecord(me, dev_st[u.dev]);
+        slot_dev[k] = u.dev;
+      } else {
+        err = cudaSetDevice(dev_ord[u.dev]);
+        if (err == cudaSuccess)
+          err = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, static_cast<size_t>(u.nr), cudaMemcpyHostToDevice, dev_st[u.dev]);
+        if (err == cudaSuccess && compare)      // the DMA reads the pinned source while this thread compares it with its partner
+          half_unit_pack_and_sums(src, lds, partner, lds, u.nr, u.nc, e, nullptr, true, scratch.data(), acc);
+      }
+      if (err != cudaSuccess) { failed.store(1); break; }
+      if (compare) half_unit_contribution(u, acc, &unit_diff[i], &unit_sabs[i]);
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int w = 0; w < nthreads; ++w) th.emplace_back(worker, w);
+    for (auto& t : th) t.join();
+  }
+  if (failed.load()) {
+    cudaGetLastError();
+    set_error("upload of the host matrix failed (CUDA error in a copy worker)");
+    return SPEIGEN_ERR_CUDA;
+  }
+  SPE_TRY(sync_all());            // every shard's uploaded tiles are in place before any GPU reads a peer's
+  for (Dev& d : devs) {
+    SPE_CUDA(cudaSetDevice(d.ordinal));
+    std::vector<const double*> shard_ptrs(prob.world, nullptr);
+    for (int r = 0; r < prob.world; ++r) shard_ptrs[r] = (prob.world == 1) ? d.A : d.peer_A[r];
+    SPE_TRY(launch_mirror_cov(d.A, d.a_rows, m, d.a_ld, d.lo, cplx, block, prob.world > 1 ? shard_ptrs.data() : nullptr, prob.world,
+                              rows_per_shard, d.st));
+  }
+  SPE_TRY(sync_all());
+  host_diff = 0.0;
+  host_sabs = 0.0;
+  for (size_t i = 0; i < units.size(); ++i) { host_diff += unit_diff[i]; host_sabs += unit_sabs[i]; }
+  host_verified = compare;
+  upload_half = true;
+  loaded = true;
+  return SPEIGEN_OK;
+}
+
 int Solver::load_host(const double* X) {
   const int e = 1 + cplx;
+  host_verified = false;
+  upload_half = false;
+  {
+    const char* off = getenv("SPEIGEN_HALF_UPLOAD");
+    const bool enabled = !(off && off[0] == '0');
+    const bool single_process = static_cast<int>(devs.size()) == prob.world;
+    const size_t bytes = static_cast<size_t>(m) * m * e * sizeof(double);
+    const size_t min_bytes = static_cast<size_t>(env_i64("SPEIGEN_HALF_MIN_BYTES", 32ll << 20));
+    if (enabled && !data && single_process && (prob.world == 1 || peer_ok) && prob.world <= 8 && bytes >= min_bytes) {
+      cudaPointerAttributes pa{};
+      bool pageable = true;
+      if (cudaPointerGetAttributes(&pa, X) == cudaSuccess) pageable = (pa.type == cudaMemoryTypeUnregistered);
+      cudaGetLastError();
+      // A pinned source on several GPUs is the one case where the full upload wins: every GPU pulls its rows over its own PCIe
+      // link (0.36 s / N for 20 GB) while the host compare of the half upload takes ~0.2 s whatever N (measured, 16 host cores).
+      const char* force = getenv("SPEIGEN_HALF_UPLOAD");
+      if (pageable || prob.world == 1 || (force && force[0] == '2')) return load_host_half(X, pageable && cfg_stage_uploads());
+    }
+  }
   // describe every device's shard as a 2-D copy (rows x width bytes)
   std::vector<UploadChunk> shards;
   for (size_t i = 0; i < devs.size(); ++i) {
@@ -480,6 +621,7 @@ int Solver::load_host(const double* X) {
   }
   size_t total_bytes = 0;
   for (auto& c : shards) total_bytes += c.rows * c.width;
+  g_last_upload_bytes.store(static_cast<long long>(total_bytes));
   cudaPointerAttributes pa{};
   bool pageable = true;
   if (cudaPointerGetAttributes(&pa, X) == cudaSuccess) pageable = (pa.type == cudaMemoryTypeUnregistered);
@@ -618,7 +760,9 @@ int Solver::prepare() {
                 "pass check_symmetric = 0 to trust the caller");
       return SPEIGEN_ERR_UNSUPPORTED;
     }
-    const int full = (can_check && (cfg.check_symmetric || cfg.check_na)) ? 1 : 0;
+    // host_verified: load_host_half() already evaluated isSymmetric's sums on the host against the tiles that were not uploaded
+    // (the device copy is Hermitian by construction); the device scan then only has to deliver NaN count, sum|S| and the diagonal.
+    const int full = (!host_verified && can_check && (cfg.check_symmetric || cfg.check_na)) ? 1 : 0;
     for (Dev& d : devs) {
       SPE_CUDA(cudaSetDevice(d.ordinal));
       std::vector<const double*> shard_ptrs(prob.world, nullptr);
@@ -656,11 +800,12 @@ int Solver::prepare() {
       h_scal[3] = nn;
       h_scal[4] = mn;
     }
+    if (host_verified) { h_scal[0] = host_diff; h_scal[1] = host_sabs; }   // NaN in a tile that stayed on the host shows up here
     if (cfg.check_na && (h_scal[3] > 0.0 || std::isnan(h_scal[1]))) {
       set_error("This function cannot handle NAs.");
       return SPEIGEN_ERR_NA;
     }
-    if (full && cfg.check_symmetric) {
+    if ((full || host_verified) && cfg.check_symmetric) {
       // isSymmetric.matrix: all.equal(X, Conj(t(X)), tolerance = 100 * .Machine$double.eps)   R/spEigen.R:75
       const double tol = 100.0 * 2.220446049250313e-16;
       const double diff = h_scal[0], sabs = h_scal[1];
@@ -1484,6 +1629,7 @@ int Solver::load_device_rows(int li, int64_t row0, int64_t nrows, const double* 
                              static_cast<size_t>(nrows), cudaMemcpyDeviceToDevice, d.st));
   SPE_CUDA(cudaStreamSynchronize(d.st));
   loaded = true;
+  host_verified = false;
   return SPEIGEN_OK;
 }
 
@@ -1495,6 +1641,7 @@ int Solver::load_device(int li, const double* src, int64_t src_ld) {
                              static_cast<size_t>(d.a_rows), cudaMemcpyDeviceToDevice, d.st));
   SPE_CUDA(cudaStreamSynchronize(d.st));
   loaded = true;
+  host_verified = false;
   return SPEIGEN_OK;
 }
 

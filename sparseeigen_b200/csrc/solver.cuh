@@ -170,6 +170,11 @@ class Solver {
   int dots_parity = 0;
   // staged upload of pageable host matrices (load_host)
   bool upload_staged = false;                 // how the last load_host moved the data (reported in speigen_out)
+  // Hermitian-half upload (host_pack.h): one tile of every transposed pair crosses PCIe, isSymmetric is evaluated on the host
+  int load_host_half(const double* X, bool pageable);
+  bool upload_half = false;                   // the last load_host used it
+  bool host_verified = false;                 // host_diff / host_sabs hold isSymmetric's sums for the loaded matrix
+  double host_diff = 0.0, host_sabs = 0.0;
   static bool cfg_stage_uploads() { const char* e = getenv("SPEIGEN_NO_STAGING"); return !(e && e[0] == '1'); }
 
  private:
@@ -177,6 +182,7 @@ class Solver {
 };
 
 StageConsts make_stage(double p, double eps);
+long long last_upload_bytes();   // bytes the most recent load_host of this process moved host -> device
 
 }  // namespace speigen
 

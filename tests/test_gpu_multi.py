@@ -111,3 +111,48 @@ def test_sharded_validation_scan():
     cfg = sb.default_cfg(n_gpus=2)
     rc = sb.lib().speigen_run_f64(Sn.ctypes.data_as(sb._dp), 500, 500, 0, 3.0, 0.5, None, None, 1e-9, C.byref(cfg), C.byref(ob.c))
     assert rc == 2
+
+
+@need2
+@pytest.mark.parametrize("cplx", [False, True])
+def test_half_upload_row_sharded(cplx):
+    """Hermitian-half upload with S row-sharded inside one process: every GPU uploads one tile of each transposed pair of its
+    row block and rebuilds the others from the peers' shards over NVLink (k_mirror_cov) - same bits as the full upload."""
+    import os
+    rng = np.random.default_rng(11)
+    m, q = 1037, 6
+    A = rng.standard_normal((m, m)) + (1j * rng.standard_normal((m, m)) if cplx else 0)
+    S = A @ np.conj(A.T) / m + np.eye(m)
+    S = (S + np.conj(S.T)) / 2                                # exactly Hermitian, positive definite
+    U = rng.standard_normal((m, q)) + (1j * rng.standard_normal((m, q)) if cplx else 0)
+    P = min(_ngpu(), 4)
+    old = {k: os.environ.get(k) for k in ("SPEIGEN_HALF_UPLOAD", "SPEIGEN_HALF_MIN_BYTES", "SPEIGEN_HALF_BLOCK")}
+    try:
+        os.environ["SPEIGEN_HALF_UPLOAD"] = "0"
+        with sb.Solver(m, q, is_complex=cplx, world=P, local_gpus=P) as s:
+            s.init_comm(None)
+            s.load(S)
+            Y0 = s.contract(U)
+        os.environ["SPEIGEN_HALF_UPLOAD"] = "1"
+        os.environ["SPEIGEN_HALF_MIN_BYTES"] = "1"
+        for block in (64, 100, 2048):
+            os.environ["SPEIGEN_HALF_BLOCK"] = str(block)
+            with sb.Solver(m, q, is_complex=cplx, world=P, local_gpus=P) as s:
+                s.init_comm(None)
+                s.load(S)
+                Y1 = s.contract(U)
+                s.prepare()                                   # validation on the host sums + the device scan of the rebuilt shards
+            assert np.array_equal(Y0, Y1), block
+            Sbad = S.copy(); Sbad[900, 17] += 1e-3            # the offending tile stays on the host for some blocks, travels for others
+            with sb.Solver(m, q, is_complex=cplx, world=P, local_gpus=P) as s:
+                s.init_comm(None)
+                s.load(Sbad)
+                with pytest.raises(sb.SpEigenError, match="not symmetric"):
+                    s.prepare()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert np.linalg.norm(Y0 - S @ U) / np.linalg.norm(S @ U) < 1e-13

@@ -498,6 +498,97 @@ def test_device_side_waits_are_bounded():
     assert r["vectors"].shape == (300, 3)
 
 
+# ---------------------------------------------------------------------------------------------------
+# Hermitian-half upload (host_pack.h, Solver::load_host_half): one tile of every transposed pair crosses PCIe, the other is
+# rebuilt on the device; isSymmetric / anyNA (R/spEigen.R:53,75) are decided on the host against the tiles that stayed there
+class _env:
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        import os
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        import os
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _upload_info(s):
+    import ctypes as C
+    v = [C.c_int32() for _ in range(3)]
+    assert s.L.speigen_solver_upload_info(s.h, *[C.byref(x) for x in v]) == 0
+    return dict(staged=v[0].value, half=v[1].value, host_verified=v[2].value)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("no_staging", [0, 1])
+def test_half_upload_rebuilds_the_matrix(cplx, no_staging):
+    rng = np.random.default_rng(77)
+    m, q = 1037, 6
+    S = herm(rng, m, cplx)
+    U = panel(rng, m, q, cplx)
+    with _env(SPEIGEN_HALF_UPLOAD=0):
+        with sb.Solver(m, q, is_complex=cplx) as s:
+            s.load(S)
+            assert _upload_info(s)["half"] == 0
+            Y0 = s.contract(U)
+    for block in (96, 100, 2048):        # ragged super-tiles, tiles off the 32-element grid, a single (diagonal) super-tile
+        with _env(SPEIGEN_HALF_MIN_BYTES=1, SPEIGEN_HALF_BLOCK=block, SPEIGEN_NO_STAGING=no_staging):
+            with sb.Solver(m, q, is_complex=cplx) as s:
+                s.load(S)
+                info = _upload_info(s)
+                assert info["half"] == 1 and info["host_verified"] == 1 and info["staged"] == 1 - no_staging, info
+                Y1 = s.contract(U)
+        assert np.array_equal(Y0, Y1), (block, rel(Y1, Y0))
+    assert rel(Y0, S @ U) < 1e-13
+
+
+def test_half_upload_default_threshold_and_end_to_end():
+    """Above 32 MB the half upload is the default path of the drop-in call: same bits as the full upload."""
+    X, _ = o.spiked_samples(2500, 500, 4, 0.05, seed=31)
+    S = o.sample_cov(X)
+    S = (S + S.T) / 2                     # exactly symmetric, so that both uploads leave the same bits on the device
+    with _env(SPEIGEN_HALF_UPLOAD=0):
+        a = sb.spEigen(S, 4)
+    with _env(SPEIGEN_HALF_BLOCK=512):
+        b = sb.spEigen(S, 4)
+    c = sb.spEigen(S, 4)
+    assert not a["info"]["upload_half"] and b["info"]["upload_half"] and c["info"]["upload_half"]
+    for r in (b, c):
+        assert np.array_equal(a["vectors"], r["vectors"]) and np.array_equal(a["info"]["F"], r["info"]["F"])
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_half_upload_validation_matches_the_full_upload(cplx):
+    """isSymmetric's tolerance (100 eps on sum|S - S^H| / sum|S|) and anyNA give the same verdict whichever side of the diagonal
+    the offending entry sits on - also when its tile never leaves the host."""
+    rng = np.random.default_rng(5)
+    m = 400
+    X = rng.standard_normal((3 * m, m)) + (1j * rng.standard_normal((3 * m, m)) if cplx else 0)
+    S = np.conj(X.T) @ X / (3 * m)
+    S = (S + np.conj(S.T)) / 2
+    spots = [(3, 390), (390, 3), (150, 260), (260, 150), (200, 201)]
+    for env in (dict(SPEIGEN_HALF_UPLOAD=0), dict(SPEIGEN_HALF_MIN_BYTES=1, SPEIGEN_HALF_BLOCK=64)):
+        with _env(**env):
+            for (i, j) in spots:
+                A = S.copy(); A[i, j] += 1e-3
+                with pytest.raises(sb.SpEigenError, match="not symmetric"): sb.spEigen(A, 3)
+                A = S.copy(); A[i, j] += 1e-13          # below isSymmetric's tolerance: accepted, as in R
+                assert sb.spEigen(A, 3)["vectors"].shape == (m, 3)
+                import ctypes as C
+                Sna = np.asfortranarray(S.copy()); Sna[i, j] = np.nan
+                ob = sb._OutBuffers(m, 3, cplx)
+                run = sb.lib().speigen_run_c64 if cplx else sb.lib().speigen_run_f64
+                rc = run(Sna.ctypes.data_as(sb._dp), m, m, 0, 3.0, 0.5, None, None, 1e-9, None, C.byref(ob.c))
+                assert rc == 2, (env, i, j, rc)
+
+
 def test_max_iter_ends_a_stage_not_the_schedule():
     """R/spEigen.R:151: k >= max_iter only breaks the inner loop; the remaining (p, eps) stages still run two iterations each."""
     X, _ = o.spiked_samples(400, 100, 3, 0.1, seed=12)
