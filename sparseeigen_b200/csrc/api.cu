@@ -452,6 +452,7 @@ static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data,
   int rc = s->impl.comm_ready ? SPEIGEN_OK : s->impl.init_comm_all();
   const double t0 = wall_s();
   out->seconds_setup = t0 - t_setup0;
+  s->impl.defer_host_verify = true;      // isSymmetric / anyNA of a half-uploaded S are evaluated on the host while the GPUs work
   if (rc == SPEIGEN_OK) rc = s->impl.load_host(X);
   const double t1 = wall_s();
   out->seconds_upload = t1 - t0;
@@ -460,6 +461,11 @@ static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data,
   out->seconds_prepare = wall_s() - t1;
   if (rc == SPEIGEN_OK) rc = s->impl.init_vectors(V0, out);
   if (rc == SPEIGEN_OK) rc = s->impl.run(rho, d, thres, out);
+  {
+    // the deferred host verdict comes first in the reference's order of stop()s (R/spEigen.R:53,75 precede :77,:79)
+    const int vrc = s->impl.host_verdict();
+    if (vrc != SPEIGEN_OK) rc = vrc;
+  }
   if (rc == SPEIGEN_OK && cacheable) {
     g_cached = s;
     g_cached_prob = pb;

@@ -230,6 +230,7 @@ int Solver::alloc_dev(Dev& d) {
 }
 
 void Solver::destroy() {
+  finish_host_verify();
   for (Dev& d : devs) {
     cudaSetDevice(d.ordinal);
     if (d.st) cudaStreamSynchronize(d.st);
@@ -249,6 +250,7 @@ void Solver::destroy() {
 }
 
 void Solver::reset_for_reuse() {
+  finish_host_verify();
   loaded = prepared = inited = false;
   host_verified = upload_half = false;
   scale_max = 0.0;
@@ -467,6 +469,74 @@ static int64_t env_i64(const char* name, int64_t dflt) {
 static std::atomic<long long> g_last_upload_bytes{0};
 long long last_upload_bytes() { return g_last_upload_bytes.load(); }
 
+struct Solver::HostVerify {
+  std::vector<HalfUnit> units;
+  std::vector<double> diff, sabs;
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> threads;
+};
+
+void Solver::start_host_verify(const double* X, std::vector<HalfUnit>&& units) {
+  finish_host_verify();
+  HostVerify* hv = new HostVerify();
+  hv->units = std::move(units);
+  hv->diff.assign(hv->units.size(), 0.0);
+  hv->sabs.assign(hv->units.size(), 0.0);
+  const int hw = static_cast<int>(std::thread::hardware_concurrency());
+  const int nthreads = std::max(1, std::min(24, hw - 1));       // one core stays with the thread that drives the GPUs
+  const int e = 1 + cplx;
+  const size_t lds = static_cast<size_t>(m) * e;
+  const int64_t mm = m;
+  for (int w = 0; w < nthreads; ++w)
+    hv->threads.emplace_back([hv, X, e, lds, mm]() {
+      std::vector<double> scratch(2 * 128 * 128);
+      for (;;) {
+        const size_t i = hv->next.fetch_add(1);
+        if (i >= hv->units.size()) break;
+        const HalfUnit& u = hv->units[i];
+        double acc[3] = {0.0, 0.0, 0.0};
+        half_unit_pack_and_sums(X + (static_cast<size_t>(u.r0) * mm + u.c0) * e, lds, X + (static_cast<size_t>(u.c0) * mm + u.r0) * e, lds,
+                                u.nr, u.nc, e, nullptr, true, scratch.data(), acc);
+        half_unit_contribution(u, acc, &hv->diff[i], &hv->sabs[i]);
+      }
+    });
+  verify = hv;
+}
+
+void Solver::finish_host_verify() {
+  if (!verify) return;
+  for (auto& t : verify->threads) t.join();
+  host_diff = 0.0;
+  host_sabs = 0.0;
+  for (size_t i = 0; i < verify->units.size(); ++i) { host_diff += verify->diff[i]; host_sabs += verify->sabs[i]; }
+  host_verified = true;
+  delete verify;
+  verify = nullptr;
+}
+
+// anyNA (R/spEigen.R:53) and isSymmetric.matrix (:75) on the host sums of the Hermitian-half upload
+static int judge_host_sums(const speigen_cfg& cfg, double diff, double sabs) {
+  if (cfg.check_na && (std::isnan(sabs) || std::isnan(diff))) {
+    set_error("This function cannot handle NAs.");
+    return SPEIGEN_ERR_NA;
+  }
+  if (cfg.check_symmetric) {
+    const double tol = 100.0 * 2.220446049250313e-16;
+    const bool sym = (sabs > 0.0) ? (diff / sabs <= tol) : (diff == 0.0);
+    if (!sym) {
+      set_error("The covariance matrix is not symmetric.");
+      return SPEIGEN_ERR_NOT_SYMMETRIC;
+    }
+  }
+  return SPEIGEN_OK;
+}
+
+int Solver::host_verdict() {
+  if (!verify) return SPEIGEN_OK;
+  finish_host_verify();
+  return judge_host_sums(cfg, host_diff, host_sabs);
+}
+
 int Solver::load_host_half(const double* X, bool pageable) {
   const int e = 1 + cplx;
   const int64_t block = env_i64("SPEIGEN_HALF_BLOCK", kHalfBlock);
@@ -474,7 +544,11 @@ int Solver::load_host_half(const double* X, bool pageable) {
   std::vector<std::pair<int64_t, int64_t>> ranges;
   for (Dev& d : devs) ranges.emplace_back(d.lo, d.hi);
   const std::vector<HalfUnit> units = plan_half_upload(m, e, ranges, block, slot_bytes);
-  const bool compare = cfg.check_symmetric || cfg.check_na;
+  const bool want_compare = cfg.check_symmetric || cfg.check_na;
+  // Deferred only for a staged (pageable) source, where the pack-and-copy pass is bound by host memory traffic and dropping the
+  // partner reads shortens it (0.27 -> 0.24 s for 20 GB); a pinned source is DMA'd in place and its compare already overlaps the DMA.
+  const bool defer = defer_host_verify && want_compare && pageable;
+  const bool compare = want_compare && !defer;
   upload_staged = pageable;
   {
     long long bytes = 0;
@@ -571,11 +645,13 @@ int Solver::load_host_half(const double* X, bool pageable) {
   host_verified = compare;
   upload_half = true;
   loaded = true;
+  if (defer) start_host_verify(X, std::vector<HalfUnit>(units));
   return SPEIGEN_OK;
 }
 
 int Solver::load_host(const double* X) {
   const int e = 1 + cplx;
+  finish_host_verify();
   host_verified = false;
   upload_half = false;
   {
@@ -762,7 +838,9 @@ int Solver::prepare() {
     }
     // host_verified: load_host_half() already evaluated isSymmetric's sums on the host against the tiles that were not uploaded
     // (the device copy is Hermitian by construction); the device scan then only has to deliver NaN count, sum|S| and the diagonal.
-    const int full = (!host_verified && can_check && (cfg.check_symmetric || cfg.check_na)) ? 1 : 0;
+    if (verify && !defer_host_verify) finish_host_verify();
+    const bool host_side = host_verified || verify != nullptr;      // pending: the verdict is taken by host_verdict() later
+    const int full = (!host_side && can_check && (cfg.check_symmetric || cfg.check_na)) ? 1 : 0;
     for (Dev& d : devs) {
       SPE_CUDA(cudaSetDevice(d.ordinal));
       std::vector<const double*> shard_ptrs(prob.world, nullptr);

@@ -12,6 +12,7 @@
 #include "matrix_ops.cuh"
 #include "tail.cuh"
 #include "nccl_shim.h"
+#include "host_pack.h"
 
 namespace speigen {
 
@@ -172,6 +173,15 @@ class Solver {
   bool upload_staged = false;                 // how the last load_host moved the data (reported in speigen_out)
   // Hermitian-half upload (host_pack.h): one tile of every transposed pair crosses PCIe, isSymmetric is evaluated on the host
   int load_host_half(const double* X, bool pageable);
+  // One-shot calls defer the host's isSymmetric / anyNA evaluation: the upload only packs and copies, worker threads then
+  // compare the tile pairs in host memory WHILE the GPUs run the initialiser and the MM loop, and the verdict is taken before
+  // the call returns (an NA / "not symmetric" verdict overrides whatever the device path reported, the order of R/spEigen.R:53,75).
+  bool defer_host_verify = false;
+  struct HostVerify;
+  HostVerify* verify = nullptr;               // pending background evaluation (nullptr: none)
+  void start_host_verify(const double* X, std::vector<HalfUnit>&& units);
+  void finish_host_verify();                  // joins the workers, fills host_diff / host_sabs, sets host_verified
+  int host_verdict();                         // finish + the checks of R/spEigen.R:53,75 on the host sums (SPEIGEN_OK if none pending/failed)
   bool upload_half = false;                   // the last load_host used it
   bool host_verified = false;                 // host_diff / host_sabs hold isSymmetric's sums for the loaded matrix
   double host_diff = 0.0, host_sabs = 0.0;
