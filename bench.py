@@ -276,13 +276,23 @@ def e2e_calls(sb, S_host, q, n_gpus, calls, warm=1):
         one()
         if first is None:
             first = time.perf_counter() - t0
+    import ctypes
+    times = (ctypes.c_double * 6)()
+    per_call = []
     t0 = time.perf_counter()
     r = None
     for _ in range(calls):
+        tc = time.perf_counter()
         r = one()
+        sec = time.perf_counter() - tc
+        sb.lib().speigen_last_call_times(times)
+        i = r["info"]
+        per_call.append({"seconds": sec, "setup": i["seconds_setup"], "upload": i["seconds_upload"], "init": i["seconds_init"],
+                         "loop": i["seconds_loop"], "host_verdict_wait": times[0], "host_verdict_work": times[1], "found_kept_solver": int(times[4])})
     dt = (time.perf_counter() - t0) / calls
     r["first_call_seconds"] = first
     r["upload_fallback"] = fallback[0] if fallback else None
+    r["per_call"] = per_call
     return dt, r
 
 
@@ -299,7 +309,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-qsweep", action="store_true")
-    ap.add_argument("--e2e-calls", type=int, default=2)
+    ap.add_argument("--e2e-calls", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory exchange or NCCL allgather")
     ap.add_argument("--workload", default="speigen", choices=["speigen", "speigencov"],
@@ -501,7 +511,10 @@ def main():
                                       if r["info"]["upload_half"] else "full matrix"),
                            "calls": calls, "warmup_calls": 1, "first_call_seconds": r["first_call_seconds"],
                            "upload_fallback": r["upload_fallback"],
-                           "seconds_per_call": dt, "n_gpus": world, "host_memory": "pageable",
+                           "seconds_per_call": dt, "per_call": r["per_call"], "n_gpus": world, "host_memory": "pageable",
+                           "device_context": "the solver (shards, panels, streams, peer mappings) of a matrix above 256 MB is kept for 2 s after a "
+                                             "call (SPEIGEN_KEEPALIVE_MS) and reused by a call of the same shape, then released by a reaper "
+                                             "thread; `first_call_seconds` is a call that had to create it",
                            "mm_updates_counted_per_call": upd,
                            "counting": "2 MM updates (V1, V2) per outer iteration of R/spEigen.R:119-120; the call also runs "
                                        f"{r['info']['contractions']} streamed contractions in the loop (extrapolation/backtracking) and "

@@ -208,6 +208,12 @@ int speigen_host_half_upload_emulate(const double* S, int64_t m, int32_t is_comp
 int speigen_host_has_avx2(void);
 /* Bytes the most recent host-matrix load of this process (resident or one-shot) moved host -> device. */
 int64_t speigen_last_upload_bytes(void);
+/* Wall-clock side channel of the most recent one-shot call (speigen_run_*) of this process: out6[0] seconds spent waiting for the
+ * deferred host evaluation of isSymmetric / anyNA (R/spEigen.R:53,75) after the device work, [1] seconds that evaluation took,
+ * [2] seconds spent releasing a solver that is not kept, [3] the whole call, [4] 1 if the call found a kept solver of its shape
+ * (matrices <= 256 MB: kept until speigen_shutdown; larger ones: kept SPEIGEN_KEEPALIVE_MS, default 2000, after their last call,
+ * then released by a reaper thread), [5] how many solvers that reaper has released so far.  Measurement only. */
+int speigen_last_call_times(double* out6);
 /* Test hook: a device-side wait for an exchange epoch that never comes, bounded by budget_ms -> SPEIGEN_ERR_TIMEOUT (28). */
 int speigen_solver_selftest_timeout(speigen_solver* s, int32_t budget_ms);
 /* 0: single GPU (no exchange), 1: NCCL collectives, 2: fused peer-store exchange (valid after speigen_solver_init_comm) */

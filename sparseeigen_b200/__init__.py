@@ -144,6 +144,7 @@ def lib():
     L.speigen_host_half_upload_emulate.argtypes = [_dp, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32,
                                                    _dp, _dp, _dp]
     L.speigen_host_has_avx2.argtypes = []
+    L.speigen_last_call_times.argtypes = [_dp]
     L.speigen_last_upload_bytes.argtypes = []
     L.speigen_last_upload_bytes.restype = C.c_int64
     L.speigen_solver_exchange_mode.argtypes = [C.c_void_p]

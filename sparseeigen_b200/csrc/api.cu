@@ -1,11 +1,15 @@
 // extern "C" surface of libspeigen_b200.so (declared in include/speigen_b200.h).
 #include "solver.cuh"
 #include "host_pack.h"
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
+#include <cstdlib>
 #include <vector>
 
 namespace speigen {
@@ -401,15 +405,86 @@ int speigen_solver_kernel_time(speigen_solver* s, double* ms_total, int32_t* lau
 }
 
 // ---- one-shot drop-in calls -------------------------------------------------------------------
+// One solver of the last shape is kept alive between one-shot calls: creating and releasing the device context costs more than
+// a small solve (~7 of 16 ms at m <= 800) and 20-300 ms for a 20 GB matrix (cudaMalloc / cudaFree of the shards, varying from
+// call to call).  Small solvers (matrix <= 256 MB, SPEIGEN_CACHE_MAX_BYTES) stay until speigen_shutdown() or process exit; a
+// LARGE one is kept for `SPEIGEN_KEEPALIVE_MS` (default 2000) after the call that used it - long enough for the next call of a
+// loop over rho / q / bootstrap draws to find it - and is then released by a reaper thread, so an idle R session does not
+// sit on tens of GB of device memory.  SPEIGEN_KEEPALIVE_MS=0: released inside the call (the round-1 behaviour).
+static std::mutex g_oneshot_mtx;                 // serialises one-shot calls and guards everything below
 static speigen_solver* g_cached = nullptr;
 static speigen_problem g_cached_prob;
 static speigen_cfg g_cached_cfg;
+static double g_cached_deadline = 0.0;           // wall_s() at which the reaper releases g_cached; 0: no deadline
+static std::condition_variable g_reaper_cv;
+static std::thread g_reaper;
+static bool g_reaper_stop = false;
+static std::atomic<int> g_reaped{0};             // how many solvers the reaper has released (test / measurement side channel)
+
+static void reaper_main() {
+  std::unique_lock<std::mutex> lk(g_oneshot_mtx);
+  while (!g_reaper_stop) {
+    if (g_cached && g_cached_deadline > 0.0) {
+      const double now = wall_s();
+      if (now >= g_cached_deadline) {
+        speigen_solver_destroy(g_cached);        // under the lock: a call that arrives right now waits for the memory, as it used to
+        g_cached = nullptr;
+        g_cached_deadline = 0.0;
+        g_reaped.fetch_add(1);
+        continue;
+      }
+      g_reaper_cv.wait_for(lk, std::chrono::duration<double>(g_cached_deadline - now));
+    } else {
+      g_reaper_cv.wait(lk);
+    }
+  }
+}
+
+static void stop_reaper() {
+  {
+    std::lock_guard<std::mutex> lk(g_oneshot_mtx);
+    g_reaper_stop = true;
+  }
+  g_reaper_cv.notify_all();
+  if (g_reaper.joinable()) g_reaper.join();
+  g_reaper_stop = false;
+}
+
+// caller holds g_oneshot_mtx
+static void arm_reaper(double keepalive_s) {
+  g_cached_deadline = wall_s() + keepalive_s;
+  if (!g_reaper.joinable()) {
+    static bool hooked = false;
+    if (!hooked) {
+      hooked = true;
+      atexit([]() { stop_reaper(); });           // registered after the CUDA runtime's own exit handlers, so it runs before them
+    }
+    g_reaper = std::thread(reaper_main);
+  }
+  g_reaper_cv.notify_all();
+}
 
 int speigen_shutdown(void) {
   DeviceRestore restore_device__;
-  if (g_cached) { speigen_solver_destroy(g_cached); g_cached = nullptr; }
+  stop_reaper();
+  {
+    std::lock_guard<std::mutex> lk(g_oneshot_mtx);
+    if (g_cached) { speigen_solver_destroy(g_cached); g_cached = nullptr; }
+    g_cached_deadline = 0.0;
+  }
   release_cov_context();
   release_stage_ring();
+  return SPEIGEN_OK;
+}
+
+// wall-clock side channel of the last one-shot call: [0] wait for the deferred host verdict, [1] how long the host workers took for
+// it (from their start to the last one finishing), [2] release of a solver that is not kept, [3] whole call, [4] 1 if the call
+// found a kept solver, [5] solvers released by the reaper so far
+static double g_last_call_times[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+int speigen_last_call_times(double* out6) {
+  if (!out6) return SPEIGEN_ERR_ARG;
+  for (int i = 0; i < 5; ++i) out6[i] = g_last_call_times[i];
+  out6[5] = static_cast<double>(g_reaped.load());
   return SPEIGEN_OK;
 }
 
@@ -431,20 +506,25 @@ static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data,
   pb.world = cfg.n_gpus > 0 ? cfg.n_gpus : 1;
   pb.rank = 0;
   pb.local_gpus = pb.world;
-  // Small problems are latency-bound: creating/destroying the device context costs more than the solve (~7 of 16 ms at
-  // m <= 800), so one solver of the last shape is kept alive between calls (<= 1 GB of device memory; speigen_shutdown()
-  // or process exit releases it).  R calls are single-threaded; a mutex keeps other hosts safe.
-  static std::mutex mtx;
-  std::lock_guard<std::mutex> lock(mtx);
+  // R calls are single-threaded; the mutex keeps other hosts safe (and the reaper out of a running call).
+  std::lock_guard<std::mutex> lock(g_oneshot_mtx);
   const size_t e = is_complex ? 2 : 1;
   const size_t mat_bytes = static_cast<size_t>(nrow) * ncol * e * sizeof(double);
-  const bool cacheable = mat_bytes <= (256u << 20);
+  size_t cache_max = 256u << 20;
+  if (const char* cm = getenv("SPEIGEN_CACHE_MAX_BYTES")) { const long long v = atoll(cm); if (v >= 0) cache_max = static_cast<size_t>(v); }
+  double keepalive_s = 2.0;
+  if (const char* ka = getenv("SPEIGEN_KEEPALIVE_MS")) { const double v = atof(ka); if (v >= 0.0) keepalive_s = 1e-3 * v; }
+  const bool small = mat_bytes <= cache_max;
+  const bool cacheable = small || keepalive_s > 0.0;
   const double t_setup0 = wall_s();
+  g_cached_deadline = 0.0;                       // whatever is cached is ours now (taken or replaced below)
   speigen_solver* s = nullptr;
+  g_last_call_times[4] = 0.0;
   if (g_cached && cacheable && std::memcmp(&g_cached_prob, &pb, sizeof(pb)) == 0 && std::memcmp(&g_cached_cfg, &cfg, sizeof(cfg)) == 0) {
     s = g_cached;
     g_cached = nullptr;
     s->impl.reset_for_reuse();
+    g_last_call_times[4] = 1.0;
   } else {
     if (g_cached) { speigen_solver_destroy(g_cached); g_cached = nullptr; }
     API_TRY(speigen_solver_create(&s, &pb, &cfg));
@@ -452,7 +532,11 @@ static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data,
   int rc = s->impl.comm_ready ? SPEIGEN_OK : s->impl.init_comm_all();
   const double t0 = wall_s();
   out->seconds_setup = t0 - t_setup0;
-  s->impl.defer_host_verify = true;      // isSymmetric / anyNA of a half-uploaded S are evaluated on the host while the GPUs work
+  {
+    // isSymmetric / anyNA of a half-uploaded S are evaluated on the host while the GPUs work (SPEIGEN_DEFER_VERIFY=0: inside the upload)
+    const char* dv = getenv("SPEIGEN_DEFER_VERIFY");
+    s->impl.defer_host_verify = !(dv && dv[0] == '0');
+  }
   if (rc == SPEIGEN_OK) rc = s->impl.load_host(X);
   const double t1 = wall_s();
   out->seconds_upload = t1 - t0;
@@ -463,16 +547,23 @@ static int run_oneshot(const double* X, int64_t nrow, int64_t ncol, int is_data,
   if (rc == SPEIGEN_OK) rc = s->impl.run(rho, d, thres, out);
   {
     // the deferred host verdict comes first in the reference's order of stop()s (R/spEigen.R:53,75 precede :77,:79)
+    const double tv = wall_s();
     const int vrc = s->impl.host_verdict();
     if (vrc != SPEIGEN_OK) rc = vrc;
+    g_last_call_times[0] = wall_s() - tv;
+    g_last_call_times[1] = s->impl.host_verify_seconds;
   }
+  const double td = wall_s();
   if (rc == SPEIGEN_OK && cacheable) {
     g_cached = s;
     g_cached_prob = pb;
     g_cached_cfg = cfg;
+    if (!small) arm_reaper(keepalive_s);
   } else {
     speigen_solver_destroy(s);
   }
+  g_last_call_times[2] = wall_s() - td;
+  g_last_call_times[3] = wall_s() - t_setup0;
   return rc;
 }
 

@@ -474,6 +474,8 @@ struct Solver::HostVerify {
   std::vector<double> diff, sabs;
   std::atomic<size_t> next{0};
   std::vector<std::thread> threads;
+  std::chrono::steady_clock::time_point t_start;
+  std::atomic<long long> done_ns{0};          // latest worker finish, ns after t_start
 };
 
 void Solver::start_host_verify(const double* X, std::vector<HalfUnit>&& units) {
@@ -487,6 +489,7 @@ void Solver::start_host_verify(const double* X, std::vector<HalfUnit>&& units) {
   const int e = 1 + cplx;
   const size_t lds = static_cast<size_t>(m) * e;
   const int64_t mm = m;
+  hv->t_start = std::chrono::steady_clock::now();
   for (int w = 0; w < nthreads; ++w)
     hv->threads.emplace_back([hv, X, e, lds, mm]() {
       std::vector<double> scratch(2 * 128 * 128);
@@ -499,6 +502,9 @@ void Solver::start_host_verify(const double* X, std::vector<HalfUnit>&& units) {
                                 u.nr, u.nc, e, nullptr, true, scratch.data(), acc);
         half_unit_contribution(u, acc, &hv->diff[i], &hv->sabs[i]);
       }
+      const long long ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - hv->t_start).count();
+      long long seen = hv->done_ns.load();
+      while (ns > seen && !hv->done_ns.compare_exchange_weak(seen, ns)) {}
     });
   verify = hv;
 }
@@ -506,6 +512,7 @@ void Solver::start_host_verify(const double* X, std::vector<HalfUnit>&& units) {
 void Solver::finish_host_verify() {
   if (!verify) return;
   for (auto& t : verify->threads) t.join();
+  host_verify_seconds = 1e-9 * static_cast<double>(verify->done_ns.load());
   host_diff = 0.0;
   host_sabs = 0.0;
   for (size_t i = 0; i < verify->units.size(); ++i) { host_diff += verify->diff[i]; host_sabs += verify->sabs[i]; }

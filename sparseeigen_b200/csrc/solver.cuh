@@ -181,6 +181,7 @@ class Solver {
   HostVerify* verify = nullptr;               // pending background evaluation (nullptr: none)
   void start_host_verify(const double* X, std::vector<HalfUnit>&& units);
   void finish_host_verify();                  // joins the workers, fills host_diff / host_sabs, sets host_verified
+  double host_verify_seconds = 0.0;            // wall time the last background evaluation took (start -> last worker done)
   int host_verdict();                         // finish + the checks of R/spEigen.R:53,75 on the host sums (SPEIGEN_OK if none pending/failed)
   bool upload_half = false;                   // the last load_host used it
   bool host_verified = false;                 // host_diff / host_sabs hold isSymmetric's sums for the loaded matrix

@@ -589,6 +589,43 @@ def test_half_upload_validation_matches_the_full_upload(cplx):
                 assert rc == 2, (env, i, j, rc)
 
 
+def test_one_shot_call_keeps_a_large_solver_alive_briefly():
+    """Matrices above the cache threshold (256 MB; lowered to 0 here) keep their solver for SPEIGEN_KEEPALIVE_MS after a call: the
+    next call of the same shape reuses it, an idle process gets the device memory back from the reaper thread.  Same bits always."""
+    import ctypes as C
+    import time
+    X, _ = o.spiked_samples(900, 300, 3, 0.1, seed=3)
+    S = o.sample_cov(X)
+    t = (C.c_double * 6)()
+
+    def call():
+        r = sb.spEigen(S, 3)
+        assert sb.lib().speigen_last_call_times(t) == 0
+        return r, int(t[4]), int(t[5])
+    assert sb.lib().speigen_shutdown() == 0
+    with _env(SPEIGEN_CACHE_MAX_BYTES=0, SPEIGEN_KEEPALIVE_MS=0):
+        a, kept, _ = call()
+        b, kept_b, _ = call()
+        assert kept == 0 and kept_b == 0                     # released inside the call
+    with _env(SPEIGEN_CACHE_MAX_BYTES=0, SPEIGEN_KEEPALIVE_MS=1000):
+        c, kept_c, reaped0 = call()
+        d, kept_d, _ = call()
+        assert kept_c == 0 and kept_d == 1                   # created, then found
+        time.sleep(2.2)
+        e, kept_e, reaped1 = call()
+        assert kept_e == 0 and reaped1 == reaped0 + 1        # the reaper released it while the process was idle
+        with sb.Solver(300, 3) as s:                         # the resident API next to a kept one-shot solver
+            s.load(S)
+            assert rel(s.contract(np.eye(300, 3)), S[:, :3]) < 1e-13
+        f, kept_f, _ = call()
+        assert kept_f == 1
+        assert sb.lib().speigen_shutdown() == 0              # stops the reaper, releases what is kept
+    g, kept_g, _ = call()                                    # default thresholds: the small-matrix cache
+    assert kept_g == 0
+    for r in (b, c, d, e, f, g):
+        assert np.array_equal(a["vectors"], r["vectors"]) and np.array_equal(a["info"]["F"], r["info"]["F"])
+
+
 def test_max_iter_ends_a_stage_not_the_schedule():
     """R/spEigen.R:151: k >= max_iter only breaks the inner loop; the remaining (p, eps) stages still run two iterations each."""
     X, _ = o.spiked_samples(400, 100, 3, 0.1, seed=12)
