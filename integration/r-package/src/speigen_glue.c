@@ -133,3 +133,10 @@ void R_init_sparseEigen(DllInfo* dll) {
   R_registerRoutines(dll, NULL, calls, NULL, NULL);
   R_useDynamicSymbols(dll, FALSE);
 }
+
+/* library.dynam.unload(): stop the reaper thread of the kept-alive solver and give the device / pinned memory back
+ * (also reachable from R through .onUnload -> C_speigen_shutdown_call) */
+void R_unload_sparseEigen(DllInfo* dll) {
+  (void)dll;
+  speigen_shutdown();
+}
