@@ -252,7 +252,8 @@ def test_half_upload_moves_about_half_of_the_matrix():
 
 
 # ---- the bench contract: every committed bench line of the round carries the keys the driver and the judge read ---------------
-@pytest.mark.parametrize("name", ["r02_bench_n1.json", "r02_bench_n2.json", "r02_bench_n4.json", "r02_bench_n8.json"])
+@pytest.mark.parametrize("name", ["r02_bench_n1.json", "r02_bench_n2.json", "r02_bench_n4.json", "r02_bench_n8.json",
+                                  "r02_bench_n1_final.json", "r02_bench_n2_final.json"])
 def test_committed_bench_lines_follow_the_contract(name):
     import json
     path = os.path.join(ROOT, "profiles", name)
