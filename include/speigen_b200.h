@@ -202,7 +202,8 @@ int speigen_solver_tail_diag(speigen_solver* s, double* out48);
 int speigen_solver_upload_info(speigen_solver* s, int32_t* staged, int32_t* half, int32_t* host_verified);
 /* Host-only test hooks of that upload (no GPU): the complete procedure - unit plan, staging, isSymmetric's sums
  * sum|S - S^H| and sum|S| (R/spEigen.R:75), transposed rebuild - emulated in host memory.  S, A_out: m x m column-major
- * (interleaved complex), A_out must not alias S. */
+ * (interleaved complex), A_out must not alias S.  use_simd: 0 scalar reference, 1 the fused pack-and-compare pass (AVX2 where the
+ * CPU has it), 2 the one-shot call's flow (row-wise pack without compare, the sums in a second pass over the caller's matrix). */
 int speigen_host_half_upload_emulate(const double* S, int64_t m, int32_t is_complex, int32_t world, int64_t block,
                                      int64_t slot_bytes, int32_t use_simd, double* A_out, double* diff, double* sabs);
 int speigen_host_has_avx2(void);

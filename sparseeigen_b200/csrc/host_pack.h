@@ -46,6 +46,7 @@ void hermitian_unit_sums(const double* a, size_t lda, const double* b, size_t ld
                          double* scratch, double acc[3]);
 // The worker's inner step: walk the unit in 128 x 128 sub-tiles; `stage` != nullptr: copy every sub-tile of `a` into the dense
 // staging slot (row pitch nc * e doubles, streaming stores) while it is in cache; `compare`: accumulate the sums as above.
+// `stage` without `compare` (the one-shot call defers the compare to background workers) copies whole rows instead.
 void half_unit_pack_and_sums(const double* a, size_t lda, const double* b, size_t ldb, int64_t nr, int64_t nc, int e,
                              double* stage, bool compare, double* scratch, double acc[3]);
 // same arithmetic without SIMD (reference for the tests; also the fallback on CPUs without AVX2)

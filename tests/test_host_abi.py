@@ -221,11 +221,11 @@ def test_half_upload_plan_covers_every_pair_exactly_once(cplx):
         for world in (1, 2, 3, 8):
             for block in (1, 7, 32, 100, 2048):
                 for slot in (64, 4096, 8 << 20):
-                    for simd in (0, 1):
+                    for simd in (0, 1, 2):        # 2: pack without compare, sums in a second pass (the one-shot call's deferred flow)
                         A, d, s = _emulate_half(S, world, block, slot, simd)
                         assert np.array_equal(A, S), (m, world, block, slot)
                         assert d == 0.0 and abs(s - tot) < 1e-11 * tot
-        for simd in (0, 1):                       # a non-Hermitian matrix: the sums are numpy's
+        for simd in (0, 1, 2):                    # a non-Hermitian matrix: the sums are numpy's
             A, d, s = _emulate_half(Z, 2, 32, 4096, simd)
             dref, sref = np.abs(Z - Z.conj().T).sum(), np.abs(Z).sum()
             assert abs(d - dref) < 1e-11 * dref and abs(s - sref) < 1e-11 * sref
